@@ -1,0 +1,458 @@
+// libcrnsense: handle, tables, pinned ring, batch paths.  See include/crnsense.h for the contract and
+// the reference lines each entry point replaces.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "crn_internal.h"
+#include "crn_launch.cuh"
+
+#define CRN_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return crn::fail(CRN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),  \
+                       __FILE__, __LINE__);                                                     \
+  } while (0)
+
+namespace {
+
+// Results of one launch, device side (SoA) with a pinned host mirror.
+struct ResultBuf {
+  float *d_feat = nullptr;
+  double *d_ann = nullptr;
+  int32_t *d_dec = nullptr;
+  unsigned long long *d_mask = nullptr;
+  float *h_feat = nullptr;
+  double *h_ann = nullptr;
+  int32_t *h_dec = nullptr;
+  unsigned long long *h_mask = nullptr;
+  int64_t cap = 0;
+};
+
+struct RingSlot {
+  float *h_iq = nullptr;   // pinned [K][L] complex
+  float2 *d_iq = nullptr;  // device mirror
+  ResultBuf res;
+  cudaEvent_t done = nullptr;
+  uint64_t first_frame = 0;
+  int state = 0;  // 0 free/filling, 1 in flight
+};
+
+}  // namespace
+
+struct crn_handle {
+  crn_config cfg;
+  int device = 0;
+  int num_sms = 0;
+  int stride = 0;
+  crn::sense_launch_fn launch = nullptr;
+  crn::LaunchGeometry geo;
+  crn::SenseParams base;  // everything but iq / outputs / ngroups
+  float2 *d_tw = nullptr;
+  float *d_win = nullptr;
+  cudaStream_t stream = nullptr;     // streaming path + batch_host compute
+  cudaStream_t copy_stream = nullptr;
+  int64_t launches = 0;
+  // streaming ring
+  std::vector<RingSlot> ring;
+  int fill_slot = 0, fill_frames = 0;
+  int tail_slot = 0, inflight = 0;
+  uint64_t frames_seen = 0;
+  // batch-host staging (double buffered)
+  int64_t chunk_groups = 0;
+  float *h_stage[2] = {nullptr, nullptr};
+  float2 *d_stage[2] = {nullptr, nullptr};
+  ResultBuf stage_res[2];
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
+  cudaEvent_t stage_copied[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+int alloc_results(ResultBuf &r, int64_t ngroups, int nbands) {
+  r.cap = ngroups;
+  CRN_CUDA(cudaMalloc(&r.d_feat, sizeof(float) * ngroups * nbands));
+  CRN_CUDA(cudaMalloc(&r.d_ann, sizeof(double) * ngroups * 3));
+  CRN_CUDA(cudaMalloc(&r.d_dec, sizeof(int32_t) * ngroups));
+  CRN_CUDA(cudaMalloc(&r.d_mask, sizeof(unsigned long long) * ngroups));
+  CRN_CUDA(cudaMallocHost(&r.h_feat, sizeof(float) * ngroups * nbands));
+  CRN_CUDA(cudaMallocHost(&r.h_ann, sizeof(double) * ngroups * 3));
+  CRN_CUDA(cudaMallocHost(&r.h_dec, sizeof(int32_t) * ngroups));
+  CRN_CUDA(cudaMallocHost(&r.h_mask, sizeof(unsigned long long) * ngroups));
+  return CRN_OK;
+}
+void free_results(ResultBuf &r) {
+  cudaFree(r.d_feat);
+  cudaFree(r.d_ann);
+  cudaFree(r.d_dec);
+  cudaFree(r.d_mask);
+  cudaFreeHost(r.h_feat);
+  cudaFreeHost(r.h_ann);
+  cudaFreeHost(r.h_dec);
+  cudaFreeHost(r.h_mask);
+  r = ResultBuf();
+}
+int fetch_results_async(const ResultBuf &r, int64_t n, int nbands, cudaStream_t s) {
+  CRN_CUDA(cudaMemcpyAsync(r.h_feat, r.d_feat, sizeof(float) * n * nbands, cudaMemcpyDeviceToHost, s));
+  CRN_CUDA(cudaMemcpyAsync(r.h_ann, r.d_ann, sizeof(double) * n * 3, cudaMemcpyDeviceToHost, s));
+  CRN_CUDA(cudaMemcpyAsync(r.h_dec, r.d_dec, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  CRN_CUDA(cudaMemcpyAsync(r.h_mask, r.d_mask, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, s));
+  return CRN_OK;
+}
+void unpack_result(const ResultBuf &r, int64_t i, int nbands, uint64_t first_frame, crn_result *out) {
+  memset(out, 0, sizeof(*out));
+  out->first_frame = first_frame;
+  out->decision = r.h_dec[i];
+  out->nfeat = nbands;
+  out->occupancy_mask = r.h_mask[i];
+  for (int k = 0; k < 3; k++) out->ann_out[k] = r.h_ann[3 * i + k];
+  for (int b = 0; b < nbands; b++) out->feat[b] = r.h_feat[i * nbands + b];
+}
+
+// Inter-pass twiddle tables, computed in double: pass p (Ns = product of earlier radices, radix R):
+// tw[r*Ns + q] = exp(-j 2 pi r q / (Ns R)).
+void build_twiddles(const crn::RadixPlan &rp, std::vector<float2> &tw) {
+  tw.clear();
+  auto add = [&](int ns, int r) {
+    const double step = -2.0 * M_PI / ((double)ns * (double)r);
+    for (int rr = 0; rr < r; rr++)
+      for (int q = 0; q < ns; q++) {
+        const double a = step * (double)((long long)rr * q);
+        tw.push_back(make_float2((float)cos(a), (float)sin(a)));
+      }
+  };
+  add(rp.r0, rp.r1);
+  if (rp.r2 > 1) add(rp.r0 * rp.r1, rp.r2);
+}
+
+int grid_for(const crn_handle *h, int64_t ngroups) {
+  int64_t g = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
+  if (ngroups < g) g = ngroups;
+  return (int)(g < 1 ? 1 : g);
+}
+
+int launch(crn_handle *h, const float2 *d_iq, int64_t ngroups, float *d_feat, double *d_ann,
+           int32_t *d_dec, unsigned long long *d_mask, cudaStream_t s) {
+  if (ngroups <= 0) return CRN_OK;
+  crn::SenseParams p = h->base;
+  p.iq = d_iq;
+  p.feat = d_feat;
+  p.ann = d_ann;
+  p.decision = d_dec;
+  p.mask = d_mask;
+  p.ngroups = ngroups;
+  int st = h->launch(p, h->cfg.window, h->cfg.detector, grid_for(h, ngroups), s, nullptr);
+  if (st == CRN_OK) h->launches++;
+  return st;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crn_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return crn::fail(CRN_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+int crn_create(const crn_config *cfg, crn_handle **out) {
+  if (!out) return crn::fail(CRN_ERR_INVALID, "crn_create: null out pointer");
+  *out = nullptr;
+  int st = crn_config_validate(cfg);
+  if (st != CRN_OK) return st;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return crn::fail(CRN_ERR_NO_DEVICE, "no CUDA device (%s); libcrnsense has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return crn::fail(CRN_ERR_NO_DEVICE, "device %d out of range (have %d)", cfg->device, ndev);
+  CRN_CUDA(cudaSetDevice(cfg->device));
+
+  crn_handle *h = new (std::nothrow) crn_handle();
+  if (!h) return crn::fail(CRN_ERR_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  h->stride = cfg->frame_stride > 0 ? cfg->frame_stride : cfg->frame_len;
+  if (h->cfg.ring_slots == 0) h->cfg.ring_slots = 4;
+  cudaDeviceProp prop;
+  CRN_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  h->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete h;
+    return crn::fail(CRN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                     cfg->device, prop.major, prop.minor);
+  }
+
+  switch (cfg->nfft) {
+    case 256: h->launch = crn::launch_sense_256; break;
+    case 512: h->launch = crn::launch_sense_512; break;
+    case 1024: h->launch = crn::launch_sense_1024; break;
+    case 2048: h->launch = crn::launch_sense_2048; break;
+    case 4096: h->launch = crn::launch_sense_4096; break;
+    case 8192: h->launch = crn::launch_sense_8192; break;
+    default: delete h; return crn::fail(CRN_ERR_UNSUPPORTED, "nfft %d not compiled", cfg->nfft);
+  }
+
+  // tables
+  std::vector<float2> tw;
+  build_twiddles(crn::radix_plan(cfg->nfft), tw);
+  CRN_CUDA(cudaMalloc(&h->d_tw, sizeof(float2) * tw.size()));
+  CRN_CUDA(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+  if (cfg->window == CRN_WINDOW_HANN) {
+    // liquid-dsp hann(n, N) = 0.5 - 0.5 cos(2 pi n / (N - 1)), evaluated in float like liquid does
+    std::vector<float> w(cfg->nfft);
+    for (int n = 0; n < cfg->nfft; n++)
+      w[n] = 0.5f - 0.5f * cosf((float)(2.0 * M_PI * (double)n) / (float)(cfg->nfft - 1));
+    CRN_CUDA(cudaMalloc(&h->d_win, sizeof(float) * w.size()));
+    CRN_CUDA(cudaMemcpy(h->d_win, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+  }
+
+  crn::SenseParams &b = h->base;
+  memset(&b, 0, sizeof(b));
+  b.tw = h->d_tw;
+  b.win = h->d_win;
+  b.L = cfg->frame_len;
+  b.stride = h->stride;
+  b.K = cfg->navg;
+  b.invK = 1.0f / (float)cfg->navg;
+  b.nbands = cfg->nbands;
+  b.nsegs = cfg->nsegs;
+  b.postop = cfg->postop;
+  b.decide = cfg->decide;
+  b.threshold = cfg->ann_threshold;
+  b.energy_factor = cfg->energy_factor;
+  memcpy(b.wih, cfg->ann_wih, sizeof(b.wih));
+  memcpy(b.who, cfg->ann_who, sizeof(b.who));
+  for (int s = 0; s < cfg->nsegs; s++) {
+    b.seg_band[s] = (short)cfg->segs[s].band;
+    b.seg_lo[s] = (short)cfg->segs[s].lo;
+    b.seg_hi[s] = (short)cfg->segs[s].hi;
+  }
+
+  st = h->launch(b, cfg->window, cfg->detector, 0, nullptr, &h->geo);
+  if (st != CRN_OK) { crn_destroy(h); return st; }
+  if (h->geo.ctas_per_sm < 1) {
+    crn_destroy(h);
+    return crn::fail(CRN_ERR_CUDA, "kernel %s does not fit on an SM (smem %d B)", h->geo.name, h->geo.smem_bytes);
+  }
+
+  CRN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CRN_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+
+  // streaming ring: ring_slots decisions of K frames each
+  const size_t slot_bytes = sizeof(float) * 2 * (size_t)cfg->navg * cfg->frame_len;
+  h->ring.resize(h->cfg.ring_slots);
+  for (auto &s : h->ring) {
+    CRN_CUDA(cudaMallocHost(&s.h_iq, slot_bytes));
+    CRN_CUDA(cudaMalloc(&s.d_iq, slot_bytes));
+    st = alloc_results(s.res, 1, cfg->nbands);
+    if (st != CRN_OK) { crn_destroy(h); return st; }
+    CRN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  *out = h;
+  return CRN_OK;
+}
+
+int crn_destroy(crn_handle *h) {
+  if (!h) return CRN_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  for (auto &s : h->ring) {
+    cudaFreeHost(s.h_iq);
+    cudaFree(s.d_iq);
+    free_results(s.res);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaFreeHost(h->h_stage[i]);
+    cudaFree(h->d_stage[i]);
+    free_results(h->stage_res[i]);
+    if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
+    if (h->stage_copied[i]) cudaEventDestroy(h->stage_copied[i]);
+  }
+  cudaFree(h->d_tw);
+  cudaFree(h->d_win);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return CRN_OK;
+}
+
+// ---- streaming path -------------------------------------------------------------------------------
+
+int crn_ring_acquire(crn_handle *h, float **slot) {
+  if (!h || !slot) return crn::fail(CRN_ERR_INVALID, "crn_ring_acquire: null argument");
+  RingSlot &s = h->ring[h->fill_slot];
+  if (s.state != 0) return crn::fail(CRN_ERR_OVERRUN, "ring full: %d decisions unread", h->inflight);
+  *slot = s.h_iq + 2 * (size_t)h->fill_frames * h->cfg.frame_len;
+  return CRN_OK;
+}
+
+int crn_submit(crn_handle *h, int32_t nframes) {
+  if (!h || nframes < 1) return crn::fail(CRN_ERR_INVALID, "crn_submit: bad argument");
+  if (h->fill_frames + nframes > h->cfg.navg)
+    return crn::fail(CRN_ERR_INVALID, "crn_submit: %d frames would cross a decision boundary", nframes);
+  RingSlot &s = h->ring[h->fill_slot];
+  if (s.state != 0) return crn::fail(CRN_ERR_OVERRUN, "ring full: %d decisions unread", h->inflight);
+  if (h->fill_frames == 0) s.first_frame = h->frames_seen;
+  h->fill_frames += nframes;
+  h->frames_seen += (uint64_t)nframes;
+  if (h->fill_frames < h->cfg.navg) return CRN_OK;
+  // K-th frame: ship the slot and enqueue the fused kernel (stream ordered, non blocking)
+  CRN_CUDA(cudaSetDevice(h->device));
+  const size_t slot_bytes = sizeof(float) * 2 * (size_t)h->cfg.navg * h->cfg.frame_len;
+  CRN_CUDA(cudaMemcpyAsync(s.d_iq, s.h_iq, slot_bytes, cudaMemcpyHostToDevice, h->stream));
+  crn::SenseParams p = h->base;
+  p.stride = h->cfg.frame_len;  // ring slots are packed
+  p.iq = s.d_iq;
+  p.feat = s.res.d_feat;
+  p.ann = s.res.d_ann;
+  p.decision = s.res.d_dec;
+  p.mask = s.res.d_mask;
+  p.ngroups = 1;
+  int st = h->launch(p, h->cfg.window, h->cfg.detector, 1, h->stream, nullptr);
+  if (st != CRN_OK) return st;
+  h->launches++;
+  st = fetch_results_async(s.res, 1, h->cfg.nbands, h->stream);
+  if (st != CRN_OK) return st;
+  CRN_CUDA(cudaEventRecord(s.done, h->stream));
+  s.state = 1;
+  h->inflight++;
+  h->fill_slot = (h->fill_slot + 1) % (int)h->ring.size();
+  h->fill_frames = 0;
+  return CRN_OK;
+}
+
+static int take_result(crn_handle *h, crn_result *out, bool block) {
+  if (!h || !out) return crn::fail(CRN_ERR_INVALID, "crn_poll/wait: null argument");
+  if (h->inflight == 0) return crn::fail(CRN_ERR_NOT_READY, "no decision in flight");
+  RingSlot &s = h->ring[h->tail_slot];
+  if (block) {
+    CRN_CUDA(cudaEventSynchronize(s.done));
+  } else {
+    cudaError_t e = cudaEventQuery(s.done);
+    if (e == cudaErrorNotReady) return CRN_ERR_NOT_READY;
+    if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+  }
+  unpack_result(s.res, 0, h->cfg.nbands, s.first_frame, out);
+  s.state = 0;
+  h->inflight--;
+  h->tail_slot = (h->tail_slot + 1) % (int)h->ring.size();
+  return CRN_OK;
+}
+int crn_poll(crn_handle *h, crn_result *out) { return take_result(h, out, false); }
+int crn_wait(crn_handle *h, crn_result *out) { return take_result(h, out, true); }
+
+int crn_reset(crn_handle *h) {
+  if (!h) return crn::fail(CRN_ERR_INVALID, "crn_reset: null handle");
+  h->fill_frames = 0;
+  return CRN_OK;
+}
+
+// ---- batch paths ----------------------------------------------------------------------------------
+
+int crn_sense_batch_device(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat,
+                           double *d_ann, int32_t *d_decision, uint64_t *d_mask, void *cuda_stream) {
+  if (!h || !d_iq || !d_feat || ngroups < 0)
+    return crn::fail(CRN_ERR_INVALID, "crn_sense_batch_device: bad argument");
+  CRN_CUDA(cudaSetDevice(h->device));
+  return launch(h, (const float2 *)d_iq, ngroups, d_feat, d_ann, d_decision,
+                (unsigned long long *)d_mask, (cudaStream_t)cuda_stream);
+}
+
+int crn_sense_batch_host(crn_handle *h, const float *iq, int64_t ngroups, crn_result *results) {
+  if (!h || !iq || !results || ngroups < 0)
+    return crn::fail(CRN_ERR_INVALID, "crn_sense_batch_host: bad argument");
+  if (ngroups == 0) return CRN_OK;
+  CRN_CUDA(cudaSetDevice(h->device));
+  const size_t group_floats = 2 * (size_t)h->stride * h->cfg.navg;
+  const size_t group_bytes = group_floats * sizeof(float);
+  if (h->chunk_groups == 0) {
+    // ~64 MiB chunks: large enough to amortise launch + copy latency, small enough to overlap
+    int64_t cg = (int64_t)((64u << 20) / group_bytes);
+    if (cg < 1) cg = 1;
+    h->chunk_groups = cg;
+    for (int i = 0; i < 2; i++) {
+      CRN_CUDA(cudaMallocHost(&h->h_stage[i], cg * group_bytes));
+      CRN_CUDA(cudaMalloc(&h->d_stage[i], cg * group_bytes));
+      int st = alloc_results(h->stage_res[i], cg, h->cfg.nbands);
+      if (st != CRN_OK) return st;
+      CRN_CUDA(cudaEventCreateWithFlags(&h->stage_done[i], cudaEventDisableTiming));
+      CRN_CUDA(cudaEventCreateWithFlags(&h->stage_copied[i], cudaEventDisableTiming));
+    }
+  }
+  // Is the caller's buffer already page-locked?  Then DMA straight from it.
+  cudaPointerAttributes pa;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&pa, iq) == cudaSuccess) pinned = (pa.type == cudaMemoryTypeHost);
+  else cudaGetLastError();
+
+  const int64_t cg = h->chunk_groups;
+  const int64_t nchunks = (ngroups + cg - 1) / cg;
+  int64_t pending_base[2] = {-1, -1};
+  int64_t pending_n[2] = {0, 0};
+  auto drain = [&](int b) -> int {
+    if (pending_base[b] < 0) return CRN_OK;
+    CRN_CUDA(cudaEventSynchronize(h->stage_done[b]));
+    for (int64_t i = 0; i < pending_n[b]; i++)
+      unpack_result(h->stage_res[b], i, h->cfg.nbands,
+                    (uint64_t)(pending_base[b] + i) * (uint64_t)h->cfg.navg, &results[pending_base[b] + i]);
+    pending_base[b] = -1;
+    return CRN_OK;
+  };
+  for (int64_t c = 0; c < nchunks; c++) {
+    const int b = (int)(c & 1);
+    int st = drain(b);  // buffer b free again (its kernel and readback finished)
+    if (st != CRN_OK) return st;
+    const int64_t g0 = c * cg;
+    const int64_t n = (ngroups - g0 < cg) ? (ngroups - g0) : cg;
+    const float *src = iq + g0 * group_floats;
+    if (!pinned) {
+      memcpy(h->h_stage[b], src, n * group_bytes);
+      src = h->h_stage[b];
+    }
+    CRN_CUDA(cudaMemcpyAsync(h->d_stage[b], src, n * group_bytes, cudaMemcpyHostToDevice, h->stream));
+    ResultBuf &r = h->stage_res[b];
+    st = launch(h, h->d_stage[b], n, r.d_feat, r.d_ann, r.d_dec, r.d_mask, h->stream);
+    if (st != CRN_OK) return st;
+    st = fetch_results_async(r, n, h->cfg.nbands, h->stream);
+    if (st != CRN_OK) return st;
+    CRN_CUDA(cudaEventRecord(h->stage_done[b], h->stream));
+    pending_base[b] = g0;
+    pending_n[b] = n;
+  }
+  int st = drain((int)(nchunks & 1));
+  if (st != CRN_OK) return st;
+  return drain((int)((nchunks + 1) & 1));
+}
+
+int64_t crn_launch_count(const crn_handle *h) { return h ? h->launches : 0; }
+
+int crn_get_kernel_info(const crn_handle *h, crn_kernel_info *info) {
+  if (!h || !info) return crn::fail(CRN_ERR_INVALID, "crn_get_kernel_info: null argument");
+  memset(info, 0, sizeof(*info));
+  info->nfft = h->cfg.nfft;
+  info->threads_per_frame = h->geo.threads_per_frame;
+  info->elems_per_thread = h->geo.elems_per_thread;
+  info->teams_per_cta = h->geo.teams;
+  info->threads_per_cta = h->geo.threads_per_cta;
+  info->ctas_per_sm = h->geo.ctas_per_sm;
+  info->grid = h->num_sms * h->geo.ctas_per_sm;
+  info->smem_bytes = h->geo.smem_bytes;
+  info->regs_per_thread = h->geo.regs;
+  info->num_sms = h->num_sms;
+  snprintf(info->name, sizeof(info->name), "%s", h->geo.name);
+  return CRN_OK;
+}
+
+}  // extern "C"

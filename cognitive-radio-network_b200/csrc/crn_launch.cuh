@@ -1,0 +1,87 @@
+// Per-FFT-size launcher: picks the <window, detector> instantiation of sense_kernel for one Plan.
+// Each crn_sense_n<N>.cu includes this once, so the six sizes compile in parallel.
+#pragma once
+#include <cstdio>
+#include <cstring>
+
+#include "crn_internal.h"
+#include "crn_sense_kernel.cuh"
+
+namespace crn {
+
+struct LaunchGeometry {
+  int ctas_per_sm;   // resident CTAs per SM (occupancy query)
+  int smem_bytes;
+  int regs;
+  int threads_per_cta, threads_per_frame, elems_per_thread, teams;
+  char name[64];
+};
+
+// signature shared by all sizes
+typedef int (*sense_launch_fn)(const SenseParams &prm, int window, int detector, int grid,
+                               cudaStream_t stream, LaunchGeometry *geo_only);
+
+template <class P, bool WIN, int DET>
+int launch_one(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
+  auto kern = sense_kernel<P, WIN, DET>;
+  const size_t smem = P::smem_bytes(WIN);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+  if (geo) {
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P::NT, smem);
+    if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    geo->ctas_per_sm = occ;
+    geo->smem_bytes = (int)smem;
+    geo->regs = fa.numRegs;
+    geo->threads_per_cta = P::NT;
+    geo->threads_per_frame = P::T;
+    geo->elems_per_thread = P::E;
+    geo->teams = P::TEAMS;
+    snprintf(geo->name, sizeof(geo->name), "sense_n%d_r%dx%dx%d_%s_%s", P::N, P::R0, P::R1, P::R2,
+             WIN ? "hann" : "rect", DET == DET_MAGSQ ? "magsq" : "mag");
+    return CRN_OK;
+  }
+  kern<<<grid, P::NT, smem, stream>>>(prm);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "sense kernel launch: %s", cudaGetErrorString(e));
+  return CRN_OK;
+}
+
+template <class P>
+int launch_plan(const SenseParams &prm, int window, int detector, int grid, cudaStream_t stream,
+                LaunchGeometry *geo) {
+  if (window == CRN_WINDOW_HANN) {
+    return detector == CRN_DET_MAGSQ ? launch_one<P, true, DET_MAGSQ>(prm, grid, stream, geo)
+                                     : launch_one<P, true, DET_MAG>(prm, grid, stream, geo);
+  }
+  return detector == CRN_DET_MAGSQ ? launch_one<P, false, DET_MAGSQ>(prm, grid, stream, geo)
+                                   : launch_one<P, false, DET_MAG>(prm, grid, stream, geo);
+}
+
+// one per size, defined in crn_sense_n<N>.cu
+int launch_sense_256(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
+int launch_sense_512(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
+int launch_sense_1024(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
+int launch_sense_2048(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
+int launch_sense_4096(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
+int launch_sense_8192(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
+
+// Radix plan per size, needed by the host to build the twiddle tables.
+struct RadixPlan { int n, r0, r1, r2; };
+inline RadixPlan radix_plan(int n) {
+  switch (n) {
+    case 256: return {256, 16, 16, 1};
+    case 512: return {512, 32, 16, 1};
+    case 1024: return {1024, 32, 32, 1};
+    case 2048: return {2048, 32, 8, 8};
+    case 4096: return {4096, 16, 16, 16};
+    case 8192: return {8192, 32, 16, 16};
+    default: return {0, 0, 0, 0};
+  }
+}
+
+}  // namespace crn

@@ -1,0 +1,191 @@
+// Synthetic primary-user capture generated on the GPU: stands in for the USRP so
+// the BASELINE workloads (1e9 samples = 8 GB) never cross PCIe.
+//
+// What it restates from the reference (test INPUT, not the hot path):
+//   - PU waveform: ECR transmit path  src/extensible_cognitive_radio.cpp:883-949  (ofdmflexframegen with
+//     the CRTS defaults: 64 subcarriers, cyclic prefix 16, taper 4 - src/crts.cpp:501-514; liquid's
+//     default subcarrier allocation; unit power; soft gain -12 dB - ecr.cpp:59,892), generated at
+//     1.4 MS/s (scenarios/predictive_model.cfg:39) and seen by the 13 MS/s receiver (:76).  Here the
+//     OFDM symbol is evaluated directly as a continuous-time sum of its 50 used subcarriers at the
+//     receiver's sample instants (an ideal 65/7 resampler).
+//   - hopping: CE_PU_MARKOV_Chain_Tx.cpp:88-128 / CE_Random_Behaviour_PU.cpp:47-49, one draw per
+//     dwell; the chain itself is sequential and tiny, so it is walked on the host and uploaded.
+//   - complex AWGN at the stated in-band SNR (counter-hash Box-Muller).
+// The CPU statement of the same definition is oracle/crn_oracle.c:crn_oracle_synth (test infrastructure).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "crn_internal.h"
+
+namespace {
+
+constexpr int SY_M = 64, SY_CP = 16, SY_TAPER = 4, SY_SYM = SY_M + SY_CP, SY_HALF = 25;
+constexpr int SY_RATE_NUM = 7, SY_RATE_DEN = 65;  // 1.4e6 / 13e6
+
+__host__ __device__ inline unsigned long long mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+inline unsigned long long stream_seed(unsigned long long seed, long long stream) {
+  return mix64(seed ^ mix64((unsigned long long)stream * 0xD1B54A32D192ED03ull + 1));
+}
+
+int pu_next(int mode, int cur, int r) {
+  if (mode == 2) return r % 3;                 // CE_Random_Behaviour_PU.cpp:47-49
+  if (mode == 1) return r == 0 ? 0 : 1;        // as coded: CE_PU_MARKOV_Chain_Tx.cpp:104,114,123 are always true
+  if (r == 0) return 0;                        // as documented: README.md:70-74
+  if (cur == 0) return r < 4 ? 1 : 2;
+  if (cur == 1) return r < 6 ? 1 : 2;
+  return r < 3 ? 1 : 2;
+}
+
+struct SynthParams {
+  float2 *iq;
+  const signed char *states;  // [ndwell]
+  int *group_state;           // [ngroups] or nullptr
+  unsigned long long sseed;
+  long long first, n;
+  long long dwell_samples;
+  int group_samples;
+  float gain, sigc;
+  double cyc_per_sample[3];
+};
+
+__device__ __forceinline__ void subcarrier(unsigned long long sseed, long long m, int k, float &re, float &im) {
+  if (m < 0) { re = 0.f; im = 0.f; return; }
+  const unsigned long long h = mix64(sseed ^ mix64((unsigned long long)m * 128ull + (unsigned long long)(k + 64)));
+  const float g = 0.14142135623730950f;  // 1/sqrt(50)
+  const int ak = k < 0 ? -k : k;
+  if (((ak + 4) % 8) == 0) {
+    re = (h & 1) ? g : -g;
+    im = 0.f;
+  } else {
+    const float a = g * 0.70710678118654752f;
+    re = (h & 1) ? a : -a;
+    im = (h & 2) ? a : -a;
+  }
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(const SynthParams p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    const long long s = p.first + i;
+    const int ch = p.states[s / p.dwell_samples];
+    if (p.group_state && (s % p.group_samples) == 0) p.group_state[s / p.group_samples - p.first / p.group_samples] = ch;
+    const long long un = s * SY_RATE_NUM;
+    const long long m = un / ((long long)SY_RATE_DEN * SY_SYM);
+    const float tau = (float)(un % ((long long)SY_RATE_DEN * SY_SYM)) / (float)SY_RATE_DEN;
+    const float th = (tau - (float)SY_CP) * (1.0f / SY_M);
+    float zr, zi;
+    sincosf(6.283185307179586f * th, &zi, &zr);
+    float ramp = 1.0f;
+    const bool in_taper = tau < (float)SY_TAPER;
+    if (in_taper) {
+      const float sn = sinf(1.5707963267948966f * tau * (1.0f / SY_TAPER));
+      ramp = sn * sn;
+    }
+    float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f, pr = zr, pi = zi;
+#pragma unroll 5
+    for (int k = 1; k <= SY_HALF; k++) {
+      float xr, xi, yr, yi;
+      subcarrier(p.sseed, m, k, xr, xi);
+      subcarrier(p.sseed, m, -k, yr, yi);
+      ar += xr * pr - xi * pi + yr * pr + yi * pi;
+      ai += xr * pi + xi * pr - yr * pi + yi * pr;
+      if (in_taper) {
+        subcarrier(p.sseed, m - 1, k, xr, xi);
+        subcarrier(p.sseed, m - 1, -k, yr, yi);
+        br += xr * pr - xi * pi + yr * pr + yi * pi;
+        bi += xr * pi + xi * pr - yr * pi + yi * pr;
+      }
+      const float nr = pr * zr - pi * zi;
+      pi = pr * zi + pi * zr;
+      pr = nr;
+    }
+    const float vr = p.gain * (ramp * ar + (1.0f - ramp) * br);
+    const float vi = p.gain * (ramp * ai + (1.0f - ramp) * bi);
+    const double cyc = (double)s * p.cyc_per_sample[ch];
+    const float ph = (float)(cyc - floor(cyc));
+    float cr, ci;
+    sincosf(6.283185307179586f * ph, &ci, &cr);
+    float outr = vr * cr - vi * ci, outi = vr * ci + vi * cr;
+    const unsigned long long h = mix64(p.sseed ^ mix64(2ull * (unsigned long long)s + 1ull));
+    const float u1 = (float)((h >> 40) + 1ull) * (1.0f / 16777216.0f);
+    const float u2 = (float)((h >> 16) & 0xFFFFFFull) * (1.0f / 16777216.0f);
+    const float rad = p.sigc * sqrtf(-2.0f * logf(u1));
+    float nc, ns;
+    sincosf(6.283185307179586f * u2, &ns, &nc);
+    outr += rad * nc;
+    outi += rad * ns;
+    p.iq[i] = make_float2(outr, outi);
+  }
+}
+
+}  // namespace
+
+extern "C" int crn_synth_generate_device(const crn_synth_config *sc, int32_t device, void *d_iq,
+                                         int64_t first_sample, int64_t nsamples, int32_t *d_state,
+                                         void *cuda_stream) {
+  if (!sc || !d_iq || first_sample < 0 || nsamples < 0 || sc->group_samples < 1 || sc->dwell_groups < 1)
+    return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_device: bad argument");
+  if (d_state && (first_sample % sc->group_samples) != 0)
+    return crn::fail(CRN_ERR_INVALID, "first_sample must be group aligned when d_state is requested");
+  if (nsamples == 0) return CRN_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return crn::fail(CRN_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+
+  SynthParams p;
+  memset(&p, 0, sizeof(p));
+  p.iq = (float2 *)d_iq;
+  p.group_state = d_state;
+  p.sseed = stream_seed(sc->seed, 0);
+  p.first = first_sample;
+  p.n = nsamples;
+  p.dwell_samples = (long long)sc->dwell_groups * sc->group_samples;
+  p.group_samples = sc->group_samples;
+  p.gain = (float)pow(10.0, sc->pu_gain_db / 20.0);
+  const double ps = pow(10.0, sc->pu_gain_db / 10.0);
+  const double bocc = (2.0 * SY_HALF + 1.0) / SY_M * sc->pu_rate;
+  const double sigma2 = ps * sc->fs / (bocc * pow(10.0, sc->snr_db / 10.0));
+  p.sigc = (float)sqrt(sigma2 / 2.0);
+  for (int c = 0; c < 3; c++) p.cyc_per_sample[c] = sc->offsets_hz[c] / sc->fs;
+
+  // walk the hop chain on the host from dwell 0 (it is sequential by definition) and upload it
+  const long long ndwell = (first_sample + nsamples + p.dwell_samples - 1) / p.dwell_samples;
+  std::vector<signed char> states((size_t)ndwell);
+  int cur = 0;  // dwell 0 on CH1: tx_freq = 833e6, scenarios/predictive_model.cfg:37
+  for (long long d = 0; d < ndwell; d++) {
+    if (d > 0) {
+      const unsigned long long h = mix64(p.sseed ^ (0xA5A5A5A5ull + (unsigned long long)d * 0x2545F4914F6CDD1Dull));
+      const int r = (sc->hop_mode == 2) ? (int)((h >> 33) % 3) : (int)((h >> 33) % 10);
+      cur = pu_next(sc->hop_mode, cur, r);
+    }
+    states[(size_t)d] = (signed char)cur;
+  }
+  signed char *d_states = nullptr;
+  e = cudaMallocAsync(&d_states, (size_t)ndwell, st);
+  if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaMallocAsync: %s", cudaGetErrorString(e));
+  e = cudaMemcpyAsync(d_states, states.data(), (size_t)ndwell, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  // pageable source: the copy is staged before the call returns, `states` may go out of scope
+  p.states = d_states;
+
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+  long long blocks = (nsamples + 255) / 256;
+  const long long cap = (long long)dev_sms * 8;
+  if (blocks > cap) blocks = cap;
+  synth_kernel<<<(int)blocks, 256, 0, st>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "synth kernel launch: %s", cudaGetErrorString(e));
+  e = cudaFreeAsync(d_states, st);
+  if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaFreeAsync: %s", cudaGetErrorString(e));
+  return CRN_OK;
+}

@@ -1,0 +1,337 @@
+/*
+ * TEST INFRASTRUCTURE ONLY (oracle/).  Never linked into libcrnsense or any product path; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * Oracle "port": plain-C restatement of the reference's sensing algorithm
+ *     cognitive_engines/CE_Predictive_Node/CE_Predictive_Node.cpp:146-261
+ * parametrised by the same crn_config the GPU library takes, so the configurations the reference
+ * cannot express (N != 512, Hann, |X|^2, K = 64, 64 sub-channels) are the same loop nest with the
+ * options flipped.  In reference-exact mode (crn_config_reference) it is checked BIT-EXACT against
+ * oracle O1 (the unmodified engine object driven by oracle/ref_harness.cpp) in tests/test_oracle.py.
+ *
+ * PARITY UNPINNED by the reference itself: it ships no tests, golden vectors or recorded IQ, and its FFT
+ * (liquid-dsp a4d7c80d3) is an absent third-party dependency restated in oracle/liquid_fft_restated.c.
+ * Pins that do come from the reference: the 43 weight literals (.cpp:78-120), the bin table
+ * (.cpp:173-190), the order of operations, and the unmodified engine object itself.
+ */
+#include <complex.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#include "../include/crnsense.h"
+
+typedef float _Complex cf32;
+typedef struct fftplan_s *fftplan;
+fftplan fft_create_plan(unsigned int n, cf32 *x, cf32 *y, int dir, int flags);
+void fft_destroy_plan(fftplan p);
+void fft_execute(fftplan p);
+
+/* liquid-dsp's hann(n, N) = 0.5 - 0.5 cos(2 pi n / (N-1)) (symmetric; src/math/src/windows.c,
+   recalled - liquid is absent).  The reference engine itself applies no window. */
+float crn_oracle_hann(int n, int N) {
+  return 0.5f - 0.5f * cosf((float)(2.0 * M_PI * (double)n) / (float)(N - 1));
+}
+
+/* One decision group: frames[K][stride] -> feat[nbands], ann[3], decision, mask. */
+static void sense_group(const crn_config *c, const float *iq, fftplan plan, cf32 *buf, cf32 *spec,
+                        float *avg, const float *win, float *feat, double *ann, int32_t *decision,
+                        uint64_t *mask) {
+  const int N = c->nfft, L = c->frame_len, K = c->navg;
+  const int stride = c->frame_stride > 0 ? c->frame_stride : L;
+  memset(avg, 0, sizeof(float) * N); /* .cpp:39,287 */
+  for (int k = 0; k < K; k++) {
+    const float *fr = iq + 2 * (size_t)k * stride;
+    /* .cpp:149: memcpy of L samples into buffer[N]; the tail stays zero */
+    for (int n = 0; n < N; n++) {
+      if (n < L) {
+        float re = fr[2 * n], im = fr[2 * n + 1];
+        if (win) { re *= win[n]; im *= win[n]; }
+        buf[n] = re + im * _Complex_I;
+      } else {
+        buf[n] = 0;
+      }
+    }
+    fft_execute(plan); /* .cpp:150 */
+    for (int i = 0; i < N; i++) { /* .cpp:152-154 */
+      float d;
+      if (c->detector == CRN_DET_MAG) {
+        d = cabsf(spec[i]);
+      } else {
+        const float re = crealf(spec[i]), im = cimagf(spec[i]);
+        d = re * re + im * im;
+      }
+      avg[i] += d / (float)K;
+    }
+  }
+  /* .cpp:163-197: per-band sums in the listed order, then the power feature */
+  float m[CRN_MAX_BANDS];
+  for (int b = 0; b < c->nbands; b++) m[b] = 0.0f;
+  for (int s = 0; s < c->nsegs; s++)
+    for (int i = c->segs[s].lo; i < c->segs[s].hi; i++) m[c->segs[s].band] += avg[i];
+  for (int b = 0; b < c->nbands; b++)
+    feat[b] = (c->postop == CRN_POST_SQUARE_OF_SUM) ? m[b] * m[b] : m[b];
+
+  double out[CRN_ANN_OUTPUTS + 1] = {0, 0, 0, 0};
+  int dec = 0;
+  uint64_t msk = 0;
+  if (c->decide == CRN_DECIDE_ANN) {
+    /* .cpp:200: Features_Buffer = {0, NF^2, CH1, CH2, CH3} == features 0..3 */
+    double F[CRN_ANN_INPUTS + 1] = {0, feat[0], feat[1], feat[2], feat[3]};
+    double H[CRN_ANN_HIDDEN + 1];
+    for (int j = 1; j <= CRN_ANN_HIDDEN; j++) { /* .cpp:214-220 */
+      double sum = c->ann_wih[0][j];
+      for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += F[i] * c->ann_wih[i][j];
+      H[j] = 1.0 / (1.0 + exp(-sum));
+    }
+    for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) { /* .cpp:229-235 */
+      double sum = c->ann_who[0][k];
+      for (int j = 1; j <= CRN_ANN_HIDDEN; j++) sum += H[j] * c->ann_who[j][k];
+      out[k] = 1.0 / (1.0 + exp(-sum));
+    }
+    /* .cpp:245-261 first-match chain */
+    if (out[1] >= c->ann_threshold) dec = CRN_CH1_OCCUPIED;
+    else if (out[2] >= c->ann_threshold) dec = CRN_CH2_OCCUPIED;
+    else if (out[3] >= c->ann_threshold) dec = CRN_CH3_OCCUPIED;
+    else dec = CRN_ALL_BUSY;
+    msk = dec ? (1ull << (dec - 1)) : 0;
+  } else if (c->decide == CRN_DECIDE_ENERGY) {
+    float mn = feat[0];
+    for (int b = 1; b < c->nbands; b++) mn = feat[b] < mn ? feat[b] : mn;
+    for (int b = 0; b < c->nbands; b++)
+      if ((double)feat[b] > c->energy_factor * (double)mn) msk |= (1ull << b);
+  }
+  if (ann) { ann[0] = out[1]; ann[1] = out[2]; ann[2] = out[3]; }
+  if (decision) *decision = dec;
+  if (mask) *mask = msk;
+}
+
+struct sense_job {
+  const crn_config *c;
+  const float *iq;
+  const float *win;
+  int64_t g0, g1;
+  float *feat;
+  double *ann;
+  int32_t *decision;
+  uint64_t *mask;
+};
+
+static void *sense_worker(void *arg) {
+  struct sense_job *j = (struct sense_job *)arg;
+  const crn_config *c = j->c;
+  const int N = c->nfft;
+  const int stride = c->frame_stride > 0 ? c->frame_stride : c->frame_len;
+  const size_t group_floats = 2 * (size_t)stride * c->navg;
+  cf32 *buf = (cf32 *)calloc(N, sizeof(cf32));
+  cf32 *spec = (cf32 *)calloc(N, sizeof(cf32));
+  float *avg = (float *)calloc(N, sizeof(float));
+  fftplan plan = fft_create_plan(N, buf, spec, +1, 0); /* .cpp:42-45 */
+  for (int64_t g = j->g0; g < j->g1; g++)
+    sense_group(c, j->iq + g * group_floats, plan, buf, spec, avg, j->win, j->feat + g * c->nbands,
+                j->ann ? j->ann + 3 * g : NULL, j->decision ? j->decision + g : NULL,
+                j->mask ? j->mask + g : NULL);
+  fft_destroy_plan(plan);
+  free(buf);
+  free(spec);
+  free(avg);
+  return NULL;
+}
+
+/* Returns 0, or -1 on bad arguments.  iq: ngroups*K frames, frame f at iq + 2*f*stride floats.
+   Groups are independent (fft_avg is zeroed per decision, .cpp:287), so nthreads > 1 splits the group
+   range into contiguous blocks, one engine state (plan + buffers) per thread. */
+int crn_oracle_sense(const crn_config *c, const float *iq, int64_t ngroups, float *feat, double *ann,
+                     int32_t *decision, uint64_t *mask, int nthreads) {
+  if (!c || !iq || !feat || c->nfft < 2 || c->frame_len > c->nfft || c->nbands < 1) return -1;
+  const int N = c->nfft;
+  float *win = NULL;
+  if (c->window == CRN_WINDOW_HANN) {
+    win = (float *)malloc(sizeof(float) * N);
+    for (int n = 0; n < N; n++) win[n] = crn_oracle_hann(n, N);
+  }
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if ((int64_t)nthreads > ngroups) nthreads = ngroups > 0 ? (int)ngroups : 1;
+  struct sense_job jobs[256];
+  pthread_t tid[256];
+  for (int t = 0; t < nthreads; t++) {
+    struct sense_job jb = {c, iq, win, ngroups * t / nthreads, ngroups * (t + 1) / nthreads,
+                           feat, ann, decision, mask};
+    jobs[t] = jb;
+  }
+  if (nthreads == 1) {
+    sense_worker(&jobs[0]);
+  } else {
+    for (int t = 0; t < nthreads; t++) pthread_create(&tid[t], NULL, sense_worker, &jobs[t]);
+    for (int t = 0; t < nthreads; t++) pthread_join(tid[t], NULL);
+  }
+  free(win);
+  return 0;
+}
+
+/* Same, timed: seconds around the group loop only. */
+double crn_oracle_time(const crn_config *c, const float *iq, int64_t ngroups, int nthreads) {
+  float *feat = (float *)malloc(sizeof(float) * (size_t)ngroups * c->nbands);
+  double *ann = (double *)malloc(sizeof(double) * 3 * (size_t)ngroups);
+  int32_t *dec = (int32_t *)malloc(sizeof(int32_t) * (size_t)ngroups);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  crn_oracle_sense(c, iq, ngroups, feat, ann, dec, NULL, nthreads);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  free(feat);
+  free(ann);
+  free(dec);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+int crn_oracle_max_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic primary-user capture (test input).  CPU statement of the generator that
+ * libcrnsense's crn_synth_generate_device runs on the GPU; both follow the definition in DESIGN.md
+ * ("Synthetic IQ").  It stands in for what the reference produces over the air:
+ *   - PU waveform: ofdmflexframegen with the CRTS defaults - 64 subcarriers, cyclic prefix 16,
+ *     taper 4 (src/crts.cpp:501-514), liquid's default subcarrier allocation (guard M/10, pilots
+ *     every 8, DC null; recalled), unit power, soft gain -12 dB
+ *     (src/extensible_cognitive_radio.cpp:59,892), generated at 1.4 MS/s
+ *     (scenarios/predictive_model.cfg:39) and observed at 13 MS/s (:76) by evaluating the OFDM symbol
+ *     as a continuous-time sum of subcarriers (an ideal resampler);
+ *   - hopping: CE_PU_MARKOV_Chain_Tx.cpp:88-128 (rand()%10 outcome -> next channel) or
+ *     CE_Random_Behaviour_PU.cpp:47-49 (rand()%3), one draw per dwell;
+ *   - complex AWGN at the stated in-band SNR.
+ * Bit-exact equality with liquid's framegen is neither possible (absent) nor needed (test input).
+ * ------------------------------------------------------------------------------------------------ */
+#define SY_M 64
+#define SY_CP 16
+#define SY_TAPER 4
+#define SY_SYM (SY_M + SY_CP)
+#define SY_HALF 25 /* used subcarriers k = -25..-1, 1..25 (M/2 - guard(6) - 1) */
+#define SY_RATE_NUM 7
+#define SY_RATE_DEN 65
+
+static uint64_t mix64(uint64_t x) { /* splitmix64 finaliser */
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+uint64_t crn_oracle_mix64(uint64_t x) { return mix64(x); }
+
+uint64_t crn_oracle_stream_seed(uint64_t seed, int64_t stream) {
+  return mix64(seed ^ mix64((uint64_t)stream * 0xD1B54A32D192ED03ull + 1));
+}
+
+/* next PU channel (0..2) given the current one and an outcome r in 0..9 */
+int crn_oracle_pu_next(int mode, int cur, int r) {
+  if (mode == 2) return r % 3; /* CE_Random_Behaviour_PU.cpp:47-49 (r is then a raw draw) */
+  if (mode == 1) return r == 0 ? 0 : 1; /* as coded: the `>=1 || <n` tests are always true (.cpp:104,114,123) */
+  /* as documented (README.md:70-74; rows = current state) */
+  if (r == 0) return 0;
+  if (cur == 0) return r < 4 ? 1 : 2;
+  if (cur == 1) return r < 6 ? 1 : 2;
+  return r < 3 ? 1 : 2;
+}
+
+/* PU channel for dwells 0..ndwell-1 of one stream; dwell 0 starts on CH1 (tx_freq = 833e6,
+   scenarios/predictive_model.cfg:37). */
+void crn_oracle_pu_states(uint64_t stream_seed, int mode, int64_t ndwell, int8_t *out) {
+  int cur = 0;
+  for (int64_t d = 0; d < ndwell; d++) {
+    if (d > 0) {
+      const uint64_t h = mix64(stream_seed ^ (0xA5A5A5A5ull + (uint64_t)d * 0x2545F4914F6CDD1Dull));
+      const int r = (mode == 2) ? (int)((h >> 33) % 3) : (int)((h >> 33) % 10);
+      cur = crn_oracle_pu_next(mode, cur, r);
+    }
+    out[d] = (int8_t)cur;
+  }
+}
+
+static void subcarrier(uint64_t sseed, int64_t m, int k, float *re, float *im) {
+  /* k in -25..25, k != 0 */
+  if (m < 0) { *re = *im = 0.0f; return; }
+  const uint64_t h = mix64(sseed ^ mix64((uint64_t)m * 128u + (uint64_t)(k + 64)));
+  const float g = 0.14142135623730950f; /* 1/sqrt(50 used subcarriers) */
+  const int ak = k < 0 ? -k : k;
+  if (((ak + 4) % 8) == 0) { /* pilot: BPSK */
+    *re = (h & 1) ? g : -g;
+    *im = 0.0f;
+  } else { /* data: QPSK */
+    const float a = g * 0.70710678118654752f;
+    *re = (h & 1) ? a : -a;
+    *im = (h & 2) ? a : -a;
+  }
+}
+
+double crn_oracle_synth_sigma2(const crn_synth_config *sc) {
+  const double ps = pow(10.0, sc->pu_gain_db / 10.0);
+  const double bocc = (2.0 * SY_HALF + 1.0) / SY_M * sc->pu_rate;
+  return ps * sc->fs / (bocc * pow(10.0, sc->snr_db / 10.0));
+}
+
+/* One stream: samples [first, first+n) -> iq (interleaved).  states: PU channel per dwell (from
+   crn_oracle_pu_states).  */
+void crn_oracle_synth(const crn_synth_config *sc, uint64_t stream_seed, const int8_t *states,
+                      float *iq, int64_t first, int64_t n) {
+  const float gain = (float)pow(10.0, sc->pu_gain_db / 20.0);
+  const float sigc = (float)sqrt(crn_oracle_synth_sigma2(sc) / 2.0);
+  const int64_t dwell_samples = (int64_t)sc->dwell_groups * sc->group_samples;
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t s = first + i;
+    const int ch = states[s / dwell_samples];
+    const int64_t un = s * SY_RATE_NUM;
+    const int64_t m = un / ((int64_t)SY_RATE_DEN * SY_SYM);
+    const float tau = (float)(un % ((int64_t)SY_RATE_DEN * SY_SYM)) / (float)SY_RATE_DEN;
+    /* z = exp(j 2 pi (tau - cp)/M) */
+    const float th = (tau - (float)SY_CP) * (1.0f / SY_M);
+    const float zr = cosf(6.283185307179586f * th), zi = sinf(6.283185307179586f * th);
+    float ramp = 1.0f;
+    const int in_taper = tau < (float)SY_TAPER;
+    if (in_taper) {
+      const float sn = sinf(1.5707963267948966f * tau * (1.0f / SY_TAPER));
+      ramp = sn * sn;
+    }
+    float ar = 0.0f, ai = 0.0f; /* current symbol */
+    float br = 0.0f, bi = 0.0f; /* previous symbol's cyclic postfix (same phases: tau+64 == tau mod 64) */
+    float pr = zr, pi = zi;     /* z^k */
+    for (int k = 1; k <= SY_HALF; k++) {
+      float xr, xi, yr, yi;
+      subcarrier(stream_seed, m, k, &xr, &xi);
+      subcarrier(stream_seed, m, -k, &yr, &yi);
+      ar += xr * pr - xi * pi + yr * pr + yi * pi;
+      ai += xr * pi + xi * pr - yr * pi + yi * pr;
+      if (in_taper) {
+        subcarrier(stream_seed, m - 1, k, &xr, &xi);
+        subcarrier(stream_seed, m - 1, -k, &yr, &yi);
+        br += xr * pr - xi * pi + yr * pr + yi * pi;
+        bi += xr * pi + xi * pr - yr * pi + yi * pr;
+      }
+      const float nr = pr * zr - pi * zi;
+      pi = pr * zi + pi * zr;
+      pr = nr;
+    }
+    float vr = gain * (ramp * ar + (1.0f - ramp) * br);
+    float vi = gain * (ramp * ai + (1.0f - ramp) * bi);
+    /* mix to the channel offset */
+    const double cyc = (double)s * (sc->offsets_hz[ch] / sc->fs);
+    const float ph = (float)(cyc - floor(cyc));
+    const float cr = cosf(6.283185307179586f * ph), ci = sinf(6.283185307179586f * ph);
+    float outr = vr * cr - vi * ci, outi = vr * ci + vi * cr;
+    /* AWGN: Box-Muller on a counter hash */
+    const uint64_t h = mix64(stream_seed ^ mix64(2 * (uint64_t)s + 1));
+    const float u1 = (float)((h >> 40) + 1) * (1.0f / 16777216.0f);
+    const float u2 = (float)((h >> 16) & 0xFFFFFF) * (1.0f / 16777216.0f);
+    const float rad = sigc * sqrtf(-2.0f * logf(u1));
+    outr += rad * cosf(6.283185307179586f * u2);
+    outi += rad * sinf(6.283185307179586f * u2);
+    iq[2 * i] = outr;
+    iq[2 * i + 1] = outi;
+  }
+}
