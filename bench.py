@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — IQ Gsamples/s sensed (window + FFT + band energy + K-frame average + ANN) on N B200s.
+
+Workload (BASELINE.json configs[1]): 1x B200 batched sensing, 3 channels + noise floor, 1024-pt FFT,
+Hann window, 64-frame Welch average, ANN predict, 1e9 complex-float samples (8 GB) resident in HBM.
+A "step" is one pass of the fused kernel over that batch (15258 decision groups, ONE kernel launch).
+With --gpus N every rank owns its own 1e9-sample shard of the capture (weak scaling, groups are
+independent, no collective on the data path).
+
+Timing: W >= 3 warm-up steps; K steps timed with CUDA events on the launching stream, bracketed by
+barrier + synchronize, max over ranks.  The input (8 GB) is 63x larger than L2, nothing is flushed.
+  value     Gsamples/s, inputs already resident in HBM
+  e2e       same metric through the C-ABI host path (crn_sense_batch_host): pinned HOST buffer,
+            host->device copies and device->host result readback inside the timed region
+  roofline  8 B/sample algorithmic bytes / measured kernel time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle port (reference algorithm, options of this workload) on the host cores, on a
+            bounded sample of the same IQ
+`--impl reference` times the reference's CPU algorithm alone (host cores, bounded sample per step).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+NFFT, NAVG = 1024, 64
+TOTAL_SAMPLES = 10 ** 9
+METRIC = "IQ Gsamples/s sensed (FFT+band energy+ANN)"
+UNIT = "Gsamples/s"
+WORKLOAD = "configs[1]: 1xB200 batched sensing, 3 channels+NF, 1024-pt FFT, Hann, 64-frame Welch average + ANN predict, 1e9 complex-float samples"
+
+
+def _oracle():
+    """bench.py may execute oracle/ only for the cpu_baseline leg and --impl reference."""
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import oracle
+    return oracle
+
+
+def workload_config(crn):
+    cfg = crn.config_welch(NFFT, NAVG)
+    ngroups = TOTAL_SAMPLES // cfg.group_samples  # 15258 full decisions, remainder dropped
+    return cfg, ngroups
+
+
+def synth_cfg(crn, cfg):
+    # Markov PU as documented (README.md:70-74), 64 decisions per dwell, SNR 10 dB, seed 12
+    return crn.synth_config(cfg.group_samples, dwell_groups=64, snr_db=10.0, seed=12, hop_mode=0)
+
+
+def base_config(extra=None):
+    c = {"workload": WORKLOAD, "nfft": NFFT, "navg": NAVG, "window": "hann(liquid, symmetric)",
+         "detector": "|X|^2", "bands": "NF,CH1,CH2,CH3 (reference bin plan x2)", "ann": "4-5-3 logistic, fp64",
+         "samples_per_gpu": None, "l2": "input 8 GB >> 126 MB L2, no flush needed",
+         "synthetic": "OFDM PU (64 sc, cp16, taper4, 1.4->13 MS/s) hopping 833/835/838 MHz by the documented Markov matrix + AWGN, SNR 10 dB, seed 12"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        inside = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in inside)
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][2]), "samples": len(inside),
+                "power_w_max": max(float(r[3]) for r in inside), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy, of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def profiled_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_leg(crn, cfg, iq_host, budget_s, threads=None):
+    """Oracle port on the host cores on a bounded sample (first groups of the same IQ).  Returns dict."""
+    oracle = _oracle()
+    nthreads = threads or oracle.port().crn_oracle_max_threads()
+    gs = cfg.group_samples
+    have = iq_host.size // gs
+    probe = min(have, max(nthreads, 8))
+    t = oracle.time_port(cfg, iq_host[: probe * gs], probe, nthreads)
+    rate = probe * gs / max(t, 1e-9)
+    n = int(min(have, max(probe, rate * budget_s // gs)))
+    t = oracle.time_port(cfg, iq_host[: n * gs], n, nthreads)
+    return {"value": n * gs / t / 1e9, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "first %d of %d decision groups (%d samples) of the same synthetic capture, %.1f s of CPU work; "
+                      "reference algorithm restated in C (oracle/crn_oracle.c, liquid-style radix-2 fp32 FFT; liquid-dsp/FFTW "
+                      "unavailable), one engine state per thread, -O2" % (n, TOTAL_SAMPLES // gs, n * gs, t),
+            "seconds": t}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores (no GPU code on this path)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import crn_b200 as crn  # config structs only
+    oracle = _oracle()
+    cfg, ngroups = workload_config(crn)
+    gs = cfg.group_samples
+    nthreads = oracle.port().crn_oracle_max_threads()
+    sc = synth_cfg(crn, cfg)
+    # bounded sample per step: ~budget seconds of all-core CPU work, whole run within a few minutes
+    total_steps = args.steps + args.warmup
+    budget = min(4.0, max(0.25, 150.0 / max(total_steps, 1)))
+    probe_groups = max(nthreads, 8)
+    iq, _ = oracle.synth(sc, probe_groups * gs)
+    t = oracle.time_port(cfg, iq, probe_groups, nthreads)
+    n = int(max(probe_groups, min(2048, (probe_groups * budget / max(t, 1e-9)))))
+    if n > probe_groups:
+        iq, _ = oracle.synth(sc, n * gs)
+    for _ in range(args.warmup):
+        oracle.time_port(cfg, iq, n, nthreads)
+    secs = [oracle.time_port(cfg, iq, n, nthreads) for _ in range(args.steps)]
+    tot = sum(secs)
+    value = args.steps * n * gs / tot / 1e9
+    sample = ("each step = first %d decision groups (%d samples) of the synthetic capture, all %d host threads, "
+              "reference algorithm restated in C with this workload's options (the unmodified engine is fixed at "
+              "N=512/K=10/no window and cannot express it)" % (n, n * gs, nthreads))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": base_config({"samples_per_step": n * gs}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    # the unmodified reference engine in its own (only) mode, for context
+    if oracle.ref() is not None:
+        rcfg = crn.config_reference()
+        rsc = crn.synth_config(rcfg.group_samples, dwell_groups=64, snr_db=10.0, seed=12)
+        rn = nthreads * 2000
+        riq, _ = oracle.synth(rsc, rn * rcfg.group_samples)
+        sec, nd = oracle.time_ref(riq, 512, rn * 10, nthreads)
+        line["reference_engine_native_mode"] = {
+            "value": rn * rcfg.group_samples / sec / 1e9, "unit": UNIT, "cores": nthreads, "kind": "reference",
+            "sample": "unmodified CE_Predictive_Node.cpp (oracle/_ref), N=512 K=10 rect |X|, %d decisions, one engine per thread" % nd}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import crn_b200 as crn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libcrnsense has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg, ngroups = workload_config(crn)
+    gs = cfg.group_samples
+    nsamp = ngroups * gs
+    stream = torch.cuda.current_stream().cuda_stream
+    sensor = crn.Sensor(cfg, device=local_rank)
+    info = sensor.kernel_info()
+
+    # ---- synthetic capture, generated in HBM (rank r owns samples [r*nsamp, (r+1)*nsamp)) -------------
+    d_iq = torch.empty(nsamp, 2, dtype=torch.float32, device=dev)
+    d_state = torch.empty(ngroups, dtype=torch.int32, device=dev)
+    crn.synth_generate(synth_cfg(crn, cfg), d_iq, rank * nsamp, nsamp, d_state, local_rank, stream)
+    d_feat = torch.empty(ngroups, cfg.nbands, dtype=torch.float32, device=dev)
+    d_ann = torch.empty(ngroups, 3, dtype=torch.float64, device=dev)
+    d_dec = torch.empty(ngroups, dtype=torch.int32, device=dev)
+    d_mask = torch.empty(ngroups, dtype=torch.int64, device=dev)
+
+    def step():
+        sensor.sense_device(d_iq, ngroups, d_feat, d_ann, d_dec, d_mask, stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = sensor.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t_wall0 = time.time()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    t_wall1 = time.time()
+    gpu_launches = sensor.launches - launches0
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = tmax.item()
+    value = world * nsamp * args.steps / (total_ms_max * 1e-3) / 1e9
+
+    # ---- parity spot check of this very batch against the oracle (outside every timed region) ----------
+    pick = sorted(set([0, ngroups // 2, ngroups - 1]))
+    iq_pick = np.concatenate([d_iq[g * gs:(g + 1) * gs].cpu().numpy().view(np.complex64).ravel() for g in pick])
+    oracle = _oracle()
+    of, oa, od, _ = oracle.sense_port(cfg, iq_pick)
+    gf, ga, gd = d_feat.cpu().numpy()[pick], d_ann.cpu().numpy()[pick], d_dec.cpu().numpy()[pick]
+    parity = {"groups": pick, "feat_max_rel": float((abs(gf - of) / abs(of)).max()),
+              "ann_max_abs": float(abs(ga - oa).max()), "decisions_equal": bool((gd == od).all())}
+    dec_hist = torch.bincount(d_dec, minlength=4)
+    if world > 1:  # optional occupancy exchange (north_star): outside the data path and the timed region
+        gathered = [torch.empty_like(dec_hist) for _ in range(world)]
+        dist.all_gather(gathered, dec_hist)
+        dec_hist = torch.stack(gathered).sum(dim=0)
+
+    # ---- end to end through the C-ABI host path: pinned host IQ -> H2D -> kernel -> D2H results --------
+    e2e = None
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_iq = torch.empty(nsamp, 2, dtype=torch.float32, pin_memory=True)
+    h_iq.copy_(d_iq)
+    torch.cuda.synchronize()
+    res = (crn.Result * ngroups)()
+    ptr = C.c_void_p(h_iq.data_ptr())
+    sensor.sense_host_raw(ptr, ngroups, res)  # warm-up: allocates the staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sensor.sense_host_raw(ptr, ngroups, res)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    hf, ha, hd, _ = crn.results_to_arrays(res, cfg.nbands)
+    e2e_ok = bool(np.array_equal(hf, d_feat.cpu().numpy()) and np.array_equal(hd, d_dec.cpu().numpy()))
+    e2e = {"value": world * nsamp * e2e_steps / e2e_t.item() / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": nsamp * 8, "d2h_bytes_per_step": ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8),
+           "steps": e2e_steps, "path": "crn_sense_batch_host (C-ABI), pinned host IQ, 64 MiB double-buffered chunks; wall clock, max over ranks",
+           "matches_device_path": e2e_ok}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same capture -----------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample_groups = 4096
+        iq_host = h_iq[: sample_groups * gs].numpy().view(np.complex64).ravel()
+        cpu = cpu_leg(crn, cfg, iq_host, args.cpu_seconds)
+    peak, peak_src = measured_peak()
+    kernel_ms = sum(step_ms) / len(step_ms)  # one launch per step: event-timed launch duration
+    achieved = nsamp * 8 / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(), "kernel": info["name"], "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": nsamp * 8, "kernel_ms": kernel_ms,
+                "note": "8 B per complex sample read once; feature write-back (%d B per launch) not counted" %
+                        (ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8))}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": base_config({"samples_per_gpu": nsamp, "groups_per_gpu": ngroups, "kernel": info}),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+            "cpu_baseline": cpu, "parity_check": parity, "decision_histogram": dec_hist.cpu().tolist(),
+            "ms_per_step_minmax": [min(step_ms), max(step_ms)]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -278,8 +278,8 @@ double crn_oracle_synth_sigma2(const crn_synth_config *sc) {
 
 /* One stream: samples [first, first+n) -> iq (interleaved).  states: PU channel per dwell (from
    crn_oracle_pu_states).  */
-void crn_oracle_synth(const crn_synth_config *sc, uint64_t stream_seed, const int8_t *states,
-                      float *iq, int64_t first, int64_t n) {
+static void synth_range(const crn_synth_config *sc, uint64_t stream_seed, const int8_t *states,
+                        float *iq, int64_t first, int64_t n) {
   const float gain = (float)pow(10.0, sc->pu_gain_db / 20.0);
   const float sigc = (float)sqrt(crn_oracle_synth_sigma2(sc) / 2.0);
   const int64_t dwell_samples = (int64_t)sc->dwell_groups * sc->group_samples;
@@ -334,4 +334,37 @@ void crn_oracle_synth(const crn_synth_config *sc, uint64_t stream_seed, const in
     iq[2 * i] = outr;
     iq[2 * i + 1] = outi;
   }
+}
+
+struct synth_job {
+  const crn_synth_config *sc;
+  uint64_t seed;
+  const int8_t *states;
+  float *iq;
+  int64_t first, n;
+};
+static void *synth_worker(void *arg) {
+  struct synth_job *j = (struct synth_job *)arg;
+  synth_range(j->sc, j->seed, j->states, j->iq, j->first, j->n);
+  return NULL;
+}
+
+/* Every sample is a pure function of its index, so the range is simply split over the host cores. */
+void crn_oracle_synth(const crn_synth_config *sc, uint64_t stream_seed, const int8_t *states,
+                      float *iq, int64_t first, int64_t n) {
+  int nt = crn_oracle_max_threads();
+  if (nt > 64) nt = 64;
+  if (n < 65536 || nt < 2) {
+    synth_range(sc, stream_seed, states, iq, first, n);
+    return;
+  }
+  struct synth_job jobs[64];
+  pthread_t tid[64];
+  for (int t = 0; t < nt; t++) {
+    const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+    struct synth_job jb = {sc, stream_seed, states, iq + 2 * a, first + a, b - a};
+    jobs[t] = jb;
+    pthread_create(&tid[t], NULL, synth_worker, &jobs[t]);
+  }
+  for (int t = 0; t < nt; t++) pthread_join(tid[t], NULL);
 }

@@ -154,16 +154,24 @@ def sense_f64(cfg, iq, ngroups=None):
     ann = np.zeros((ngroups, 3))
     dec = np.zeros(ngroups, np.int32)
     if cfg.decide == 1:
-        wih = np.array([[cfg.ann_wih[i][j] for j in range(6)] for i in range(5)])
-        who = np.array([[cfg.ann_who[j][k] for k in range(4)] for j in range(6)])
-        F = np.concatenate([np.ones((ngroups, 1)), feat[:, :4]], axis=1)  # bias at index 0
-        with np.errstate(over="ignore"):
-            H = 1.0 / (1.0 + np.exp(-(F @ wih[:, 1:])))
-            Hb = np.concatenate([np.ones((ngroups, 1)), H], axis=1)
-            ann = 1.0 / (1.0 + np.exp(-(Hb @ who[:, 1:])))
-        thr = cfg.ann_threshold
-        dec = np.where(ann[:, 0] >= thr, 1, np.where(ann[:, 1] >= thr, 2, np.where(ann[:, 2] >= thr, 3, 0))).astype(np.int32)
+        ann, dec = mlp_f64(cfg, feat)
     return feat, ann, dec
+
+
+def mlp_f64(cfg, feat):
+    """CE_Predictive_Node.cpp:200,214-261 on given features (rows = NF^2, CH1, CH2, CH3), float64."""
+    feat = np.asarray(feat, np.float64)
+    n = feat.shape[0]
+    wih = np.array([[cfg.ann_wih[i][j] for j in range(6)] for i in range(5)])
+    who = np.array([[cfg.ann_who[j][k] for k in range(4)] for j in range(6)])
+    F = np.concatenate([np.ones((n, 1)), feat[:, :4]], axis=1)  # bias at index 0
+    with np.errstate(over="ignore"):
+        H = 1.0 / (1.0 + np.exp(-(F @ wih[:, 1:])))
+        Hb = np.concatenate([np.ones((n, 1)), H], axis=1)
+        ann = 1.0 / (1.0 + np.exp(-(Hb @ who[:, 1:])))
+    thr = cfg.ann_threshold
+    dec = np.where(ann[:, 0] >= thr, 1, np.where(ann[:, 1] >= thr, 2, np.where(ann[:, 2] >= thr, 3, 0))).astype(np.int32)
+    return ann, dec
 
 
 def synth(sc, nsamples, first=0, stream=0):

@@ -1,0 +1,176 @@
+"""The oracle is pinned before it is trusted: port == unmodified reference engine (bit exact), port ==
+golden fixtures produced by the reference engine, known answers derived from the reference's literals,
+analytic DFT facts, float64 bound."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, feat_close
+
+
+def golden_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
+
+
+def test_golden_fixtures_exist():
+    assert len(golden_cases()) >= 5
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[:-4])
+def test_port_reproduces_reference_engine_fixtures_bit_exact(crn, oracle, path):
+    g = np.load(path)
+    cfg = crn.config_reference()
+    cfg.frame_len = int(g["L"])
+    feat, ann, dec, _ = oracle.sense_port(cfg, g["iq"])
+    assert np.array_equal(feat, g["feat"])          # fp32, same operations in the same order
+    assert np.array_equal(ann, g["ann"])
+    assert np.array_equal(dec, g["decision"])
+    # the retune the reference performed (CE_Predictive_Node.cpp:245-261)
+    want_tx = np.array([crn.TX_FREQ_FOR_DECISION[int(d)] or 0.0 for d in dec])
+    assert np.array_equal(want_tx, g["tx_freq"])
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[:-4])
+def test_float64_restatement_bounds_the_fixtures(crn, oracle, path):
+    g = np.load(path)
+    cfg = crn.config_reference()
+    cfg.frame_len = int(g["L"])
+    feat, ann, dec = oracle.sense_f64(cfg, g["iq"])
+    assert feat_close(feat, g["feat"], 2e-5)
+    assert np.abs(ann - g["ann"]).max() <= 1e-6
+    assert np.array_equal(dec, g["decision"])
+
+
+def test_port_equals_live_reference_engine(crn, oracle):
+    """When oracle/_ref is built (build container, or shipped prebuilt) run the reference engine itself."""
+    if oracle.ref() is None:
+        pytest.skip("oracle/_ref not built here")
+    import ctypes as C
+    n, k = C.c_int(), C.c_int()
+    oracle.ref().crn_ref_constants(C.byref(n), C.byref(k))
+    assert (n.value, k.value) == (512, 10)  # CE_Predictive_Node.hpp:31-32
+    for L, seed, snr in ((512, 21, 10.0), (363, 22, 0.0), (1, 23, 20.0), (511, 24, 20.0)):
+        gs = L * 10
+        sc = crn.synth_config(gs, dwell_groups=1, snr_db=snr, seed=seed)
+        iq, _ = oracle.synth(sc, 12 * gs)
+        cfg = crn.config_reference()
+        cfg.frame_len = L
+        f0, a0, d0, _, bins = oracle.sense_ref(iq, L=L, want_bins=True)
+        f1, a1, d1, _ = oracle.sense_port(cfg, iq)
+        assert np.array_equal(f0, f1) and np.array_equal(a0, a1) and np.array_equal(d0, d1)
+        # the engine's averaged spectrum is non-negative and its band sums give the features
+        assert (bins >= 0).all()
+        m2 = bins[:, 55:85].astype(np.float32).sum(axis=1, dtype=np.float32)
+        assert np.allclose(m2 * m2, f0[:, 2], rtol=1e-5)
+
+
+def test_ann_known_answers_from_reference_weights(crn, oracle):
+    """outputs implied by the 43 literals of CE_Predictive_Node.cpp:78-120."""
+    g = np.load(os.path.join(GOLDEN, "ref_zeros.npz"))
+    assert np.allclose(g["ann"][0], [4.78996574e-01, 4.12229629e-05, 3.35047425e-03], rtol=1e-7)
+    assert g["decision"][0] == 0 and g["tx_freq"][0] == 0.0  # ALL BUSY: no retune
+    assert np.array_equal(g["feat"][0], np.zeros(4, np.float32))
+
+    # drive the MLP alone through the port: one bin per band carries sqrt(feature)
+    def mlp(nf, c1, c2, c3):
+        cfg = crn.config_reference()
+        cfg.navg = 1
+        X = np.zeros(512, np.complex128)
+        for b, v in ((300, nf), (0, c1), (55, c2), (189, c3)):
+            X[b] = np.sqrt(v)
+        x = np.fft.ifft(X).astype(np.complex64)
+        feat, ann, dec, _ = oracle.sense_port(cfg, x)
+        assert np.allclose(feat[0], [nf, c1, c2, c3], rtol=1e-4)
+        return ann[0], int(dec[0])
+    out, dec = mlp(1e4, 1e8, 1e5, 1e5)
+    assert dec == 1 and abs(out[0] - 0.99943) < 1e-4 and out[1] < 1e-6
+    out, dec = mlp(1e4, 1e5, 1e8, 1e5)
+    assert dec == 2 and abs(out[1] - 0.99941) < 1e-4
+    out, dec = mlp(1e4, 1e5, 1e5, 1e8)
+    assert dec == 3 and abs(out[2] - 0.99947) < 1e-4
+
+
+def test_tone_fixture_is_analytic(crn):
+    """One unit tone at bin 70 for L = N = 512: |X[70]| = 512, every other bin ~0, K-average keeps it:
+    CH2 = 512^2, the other features ~0 (CE_Predictive_Node.cpp:152-154,181-183,195)."""
+    g = np.load(os.path.join(GOLDEN, "ref_tone70.npz"))
+    assert abs(g["avg_bins"][0, 70] - 512.0) < 1e-2
+    assert np.delete(g["avg_bins"][0], 70).max() < 1e-2
+    assert abs(g["feat"][0, 2] - 512.0 ** 2) / 512.0 ** 2 < 1e-5
+    assert g["decision"][0] == 2 and g["tx_freq"][0] == 833e6
+
+
+@pytest.mark.parametrize("nfft,navg,mode", [(256, 3, "ref"), (1024, 64, "welch"), (2048, 4, "welch"),
+                                             (8192, 2, "wide"), (4096, 1, "wide")])
+def test_port_vs_float64_extension_modes(crn, oracle, nfft, navg, mode):
+    if mode == "ref":
+        cfg = crn.config_reference()
+        cfg.nfft, cfg.frame_len, cfg.navg = nfft, nfft, navg
+        for i in range(cfg.nsegs):
+            cfg.segs[i].lo //= 2
+            cfg.segs[i].hi //= 2
+    elif mode == "welch":
+        cfg = crn.config_welch(nfft, navg)
+    else:
+        cfg = crn.config_wideband(nfft, navg, 64)
+    gs = cfg.group_samples
+    sc = crn.synth_config(gs, dwell_groups=1, snr_db=5.0, seed=nfft)
+    iq, _ = oracle.synth(sc, 2 * gs)
+    f1, a1, d1, m1 = oracle.sense_port(cfg, iq)
+    f2, a2, d2 = oracle.sense_f64(cfg, iq)
+    assert feat_close(f1, f2, 2e-5)
+    if cfg.decide == crn.DECIDE_ANN:
+        assert np.abs(a1 - a2).max() < 1e-6 and np.array_equal(d1, d2)
+
+
+def test_port_threads_agree(crn, oracle):
+    cfg = crn.config_welch(1024, 8)
+    sc = crn.synth_config(cfg.group_samples, dwell_groups=1)
+    iq, _ = oracle.synth(sc, 9 * cfg.group_samples)
+    a = oracle.sense_port(cfg, iq, nthreads=1)
+    b = oracle.sense_port(cfg, iq, nthreads=4)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_pu_hop_models(oracle):
+    """CE_PU_MARKOV_Chain_Tx.cpp:97-128 as coded vs README.md:70-74 as documented vs CE_Random_Behaviour_PU."""
+    nxt = oracle.port().crn_oracle_pu_next
+    for cur in range(3):
+        assert nxt(1, cur, 0) == 0 and all(nxt(1, cur, r) == 1 for r in range(1, 10))  # as coded: never CH3
+        assert nxt(0, cur, 0) == 0
+    assert [nxt(0, 0, r) for r in range(10)] == [0, 1, 1, 1, 2, 2, 2, 2, 2, 2]   # .1 .3 .6
+    assert [nxt(0, 1, r) for r in range(10)] == [0, 1, 1, 1, 1, 1, 2, 2, 2, 2]   # .1 .5 .4
+    assert [nxt(0, 2, r) for r in range(10)] == [0, 1, 1, 2, 2, 2, 2, 2, 2, 2]   # .1 .2 .7
+    assert [nxt(2, 0, r) for r in range(3)] == [0, 1, 2]
+    st = np.zeros(20000, np.int8)
+    oracle.port().crn_oracle_pu_states(oracle.port().crn_oracle_stream_seed(12, 0), 0, st.size, st.ctypes.data)
+    assert st[0] == 0
+    # empirical transition rows of the documented chain
+    for cur, row in ((0, [.1, .3, .6]), (1, [.1, .5, .4]), (2, [.1, .2, .7])):
+        idx = np.where(st[:-1] == cur)[0]
+        emp = np.bincount(st[idx + 1], minlength=3) / len(idx)
+        assert np.abs(emp - row).max() < 0.03
+
+
+def test_synth_statistics(crn, oracle):
+    """Unit-power OFDM x 10^(-12/20) at the chosen offset plus AWGN at the stated in-band SNR."""
+    gs = 65536
+    sc = crn.synth_config(gs, dwell_groups=4, snr_db=10.0, seed=5)
+    iq, states = oracle.synth(sc, 4 * gs)
+    assert states[0] == 0
+    sig2 = oracle.port().crn_oracle_synth_sigma2(__import__("ctypes").byref(sc))
+    p = np.mean(np.abs(iq) ** 2)
+    assert abs(p - (10 ** -1.2 + sig2)) / p < 0.05
+    # spectrum: PU energy sits within +-0.56 MHz of the CH1 offset (0 Hz)
+    X = np.abs(np.fft.fft(iq[: 4096 * 32].reshape(32, 4096), axis=1)) ** 2
+    psd = X.mean(axis=0)
+    hz = np.fft.fftfreq(4096, 1 / 13e6)
+    inband = psd[np.abs(hz) < 0.5e6].mean()
+    outband = psd[np.abs(hz) > 1.0e6].mean()
+    assert 8.0 < 10 * np.log10(inband / outband) < 13.0   # (S+N)/N at 10 dB in-band SNR = 10.4 dB
+    # deterministic and position independent
+    iq2, _ = oracle.synth(sc, 1000, first=gs + 17)
+    assert np.array_equal(iq2, iq[gs + 17: gs + 1017])
