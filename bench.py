@@ -134,21 +134,24 @@ def profiled_traffic():
 
 
 def cpu_leg(crn, cfg, iq_host, budget_s, threads=None):
-    """Oracle port on the host cores on a bounded sample (first groups of the same IQ).  Returns dict."""
+    """Oracle port on the host cores on a bounded sample of the same IQ: about `budget_s` seconds of
+    all-core work (whole passes over the first groups of the capture).  Returns the cpu_baseline dict."""
     oracle = _oracle()
     nthreads = threads or oracle.port().crn_oracle_max_threads()
     gs = cfg.group_samples
     have = iq_host.size // gs
-    probe = min(have, max(nthreads, 8))
+    probe = min(have, max(4 * nthreads, 32))
     t = oracle.time_port(cfg, iq_host[: probe * gs], probe, nthreads)
     rate = probe * gs / max(t, 1e-9)
     n = int(min(have, max(probe, rate * budget_s // gs)))
-    t = oracle.time_port(cfg, iq_host[: n * gs], n, nthreads)
-    return {"value": n * gs / t / 1e9, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": "first %d of %d decision groups (%d samples) of the same synthetic capture, %.1f s of CPU work; "
-                      "reference algorithm restated in C (oracle/crn_oracle.c, liquid-style radix-2 fp32 FFT; liquid-dsp/FFTW "
-                      "unavailable), one engine state per thread, -O2" % (n, TOTAL_SAMPLES // gs, n * gs, t),
-            "seconds": t}
+    passes = max(1, int(round(budget_s / (n * gs / rate))))
+    secs = sum(oracle.time_port(cfg, iq_host[: n * gs], n, nthreads) for _ in range(passes))
+    return {"value": passes * n * gs / secs / 1e9, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "%d pass(es) over the first %d of %d decision groups (%d samples per pass) of the same synthetic "
+                      "capture, %.1f s of CPU work on %d threads; reference algorithm restated in C (oracle/crn_oracle.c, "
+                      "liquid-style radix-2 fp32 FFT; liquid-dsp/FFTW unavailable), one engine state per thread, gcc -O2"
+                      % (passes, n, TOTAL_SAMPLES // gs, n * gs, secs, nthreads),
+            "seconds": secs}
 
 
 def run_reference(args):
@@ -206,6 +209,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import crn_b200 as crn
+    import importlib
+    cdist = importlib.import_module("crn_b200.dist")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,10 +267,7 @@ def run_ours(args):
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[-1])
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = tmax.item()
+    total_ms_max = cdist.max_over_ranks(total_ms, dev)
     value = world * nsamp * args.steps / (total_ms_max * 1e-3) / 1e9
 
     # ---- parity spot check of this very batch against the oracle (outside every timed region) ----------
@@ -276,11 +278,10 @@ def run_ours(args):
     gf, ga, gd = d_feat.cpu().numpy()[pick], d_ann.cpu().numpy()[pick], d_dec.cpu().numpy()[pick]
     parity = {"groups": pick, "feat_max_rel": float((abs(gf - of) / abs(of)).max()),
               "ann_max_abs": float(abs(ga - oa).max()), "decisions_equal": bool((gd == od).all())}
-    dec_hist = torch.bincount(d_dec, minlength=4)
-    if world > 1:  # optional occupancy exchange (north_star): outside the data path and the timed region
-        gathered = [torch.empty_like(dec_hist) for _ in range(world)]
-        dist.all_gather(gathered, dec_hist)
-        dec_hist = torch.stack(gathered).sum(dim=0)
+    # optional occupancy exchange (north_star): outside the data path and the timed region
+    all_dec = cdist.gather_occupancy(d_dec)          # every rank sees the whole capture's decisions
+    dec_hist = cdist.occupancy_histogram(d_dec)
+    assert all_dec.numel() == world * ngroups
 
     # ---- end to end through the C-ABI host path: pinned host IQ -> H2D -> kernel -> D2H results --------
     e2e = None
@@ -297,12 +298,10 @@ def run_ours(args):
         sensor.sense_host_raw(ptr, ngroups, res)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    e2e_t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_sec = cdist.max_over_ranks(t1 - t0, dev)
     hf, ha, hd, _ = crn.results_to_arrays(res, cfg.nbands)
     e2e_ok = bool(np.array_equal(hf, d_feat.cpu().numpy()) and np.array_equal(hd, d_dec.cpu().numpy()))
-    e2e = {"value": world * nsamp * e2e_steps / e2e_t.item() / 1e9, "unit": UNIT,
+    e2e = {"value": world * nsamp * e2e_steps / e2e_sec / 1e9, "unit": UNIT,
            "h2d_bytes_per_step": nsamp * 8, "d2h_bytes_per_step": ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8),
            "steps": e2e_steps, "path": "crn_sense_batch_host (C-ABI), pinned host IQ, 64 MiB double-buffered chunks; wall clock, max over ranks",
            "matches_device_path": e2e_ok}
@@ -315,8 +314,7 @@ def run_ours(args):
     # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same capture -----------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample_groups = 4096
-        iq_host = h_iq[: sample_groups * gs].numpy().view(np.complex64).ravel()
+        iq_host = h_iq.numpy().view(np.complex64).ravel()
         cpu = cpu_leg(crn, cfg, iq_host, args.cpu_seconds)
     peak, peak_src = measured_peak()
     kernel_ms = sum(step_ms) / len(step_ms)  # one launch per step: event-timed launch duration
