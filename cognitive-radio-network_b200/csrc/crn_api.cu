@@ -54,8 +54,8 @@ struct crn_handle {
   crn::sense_launch_fn launch = nullptr;
   crn::LaunchGeometry geo;
   crn::SenseParams base;  // everything but iq / outputs / ngroups
-  float2 *d_tw = nullptr;
-  float *d_win = nullptr;
+  float4 *d_tw = nullptr;
+  float2 *d_win = nullptr;
   cudaStream_t stream = nullptr;     // streaming path + batch_host compute
   cudaStream_t copy_stream = nullptr;
   int64_t launches = 0;
@@ -115,25 +115,60 @@ void unpack_result(const ResultBuf &r, int64_t i, int nbands, uint64_t first_fra
   for (int b = 0; b < nbands; b++) out->feat[b] = r.h_feat[i * nbands + b];
 }
 
-// Inter-pass twiddle tables, computed in double: pass p (Ns = product of earlier radices, radix R):
-// tw[r*Ns + q] = exp(-j 2 pi r q / (Ns R)).
-void build_twiddles(const crn::RadixPlan &rp, std::vector<float2> &tw) {
+// Inter-pass twiddle tables, computed in double.  Pass p (Ns = product of earlier radices, radix R)
+// multiplies input q of FFT column j by W(q, j) = exp(-j 2 pi q (j mod Ns) / (Ns R)).  The first
+// butterfly stage pairs inputs q0 and q0 + R/2, so the table stores them side by side:
+//   tw[q0*Ns + jq] = { W(q0, jq), W(q0 + R/2, jq) },  q0 < R/2, jq < Ns.
+void build_twiddles(const crn::RadixPlan &rp, std::vector<float4> &tw) {
   tw.clear();
   auto add = [&](int ns, int r) {
     const double step = -2.0 * M_PI / ((double)ns * (double)r);
-    for (int rr = 0; rr < r; rr++)
-      for (int q = 0; q < ns; q++) {
-        const double a = step * (double)((long long)rr * q);
-        tw.push_back(make_float2((float)cos(a), (float)sin(a)));
+    for (int q0 = 0; q0 < r / 2; q0++)
+      for (int jq = 0; jq < ns; jq++) {
+        const double a = step * (double)((long long)q0 * jq);
+        const double b = step * (double)((long long)(q0 + r / 2) * jq);
+        tw.push_back(make_float4((float)cos(a), (float)sin(a), (float)cos(b), (float)sin(b)));
       }
   };
   add(rp.r0, rp.r1);
   if (rp.r2 > 1) add(rp.r0 * rp.r1, rp.r2);
 }
 
+// Window in the kernel's register order: thread t of a team holds points t + T*m; the first butterfly
+// stage pairs registers m and m + E/2:  winp[m*T + t] = { w[t + T*m], w[t + T*(m + E/2)] }, m < E/2.
+// liquid-dsp hann(n, N) = 0.5 - 0.5 cos(2 pi n / (N - 1)), evaluated in float like liquid does.
+void build_window_pairs(const crn::RadixPlan &rp, std::vector<float2> &wp) {
+  const int N = rp.n, E = rp.e, T = N / E;
+  std::vector<float> w(N);
+  for (int n = 0; n < N; n++) w[n] = 0.5f - 0.5f * cosf((float)(2.0 * M_PI * (double)n) / (float)(N - 1));
+  wp.resize(N / 2);
+  for (int m = 0; m < E / 2; m++)
+    for (int t = 0; t < T; t++) wp[m * T + t] = make_float2(w[t + T * m], w[t + T * (m + E / 2)]);
+}
+
+// Reduction units per decision group: the divisor of `units` that balances the K frames best over the
+// group's teams (ties -> more units per group, i.e. fewer groups in flight per CTA and a shorter tail).
+int pick_upg(int units, int teams_per_unit, int K) {
+  int best = 1;
+  double best_eff = -1.0;
+  for (int d = 1; d <= units; d++) {
+    if (units % d) continue;
+    const int ft = d * teams_per_unit;
+    const int rounds = (K + ft - 1) / ft;
+    const double eff = (double)K / ((double)rounds * ft);
+    if (eff >= best_eff - 1e-12) {
+      best_eff = eff > best_eff ? eff : best_eff;
+      best = d;
+    }
+  }
+  return best;
+}
+
 int grid_for(const crn_handle *h, int64_t ngroups) {
   int64_t g = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
-  if (ngroups < g) g = ngroups;
+  const int64_t gl = h->geo.units / h->base.upg;  // decision groups a CTA works on at a time
+  const int64_t need = (ngroups + gl - 1) / gl;
+  if (need < g) g = need;
   return (int)(g < 1 ? 1 : g);
 }
 
@@ -203,23 +238,22 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   }
 
   // tables
-  std::vector<float2> tw;
+  std::vector<float4> tw;
   build_twiddles(crn::radix_plan(cfg->nfft), tw);
-  CRN_CUDA(cudaMalloc(&h->d_tw, sizeof(float2) * tw.size()));
-  CRN_CUDA(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+  CRN_CUDA(cudaMalloc(&h->d_tw, sizeof(float4) * tw.size()));
+  CRN_CUDA(cudaMemcpy(h->d_tw, tw.data(), sizeof(float4) * tw.size(), cudaMemcpyHostToDevice));
   if (cfg->window == CRN_WINDOW_HANN) {
-    // liquid-dsp hann(n, N) = 0.5 - 0.5 cos(2 pi n / (N - 1)), evaluated in float like liquid does
-    std::vector<float> w(cfg->nfft);
-    for (int n = 0; n < cfg->nfft; n++)
-      w[n] = 0.5f - 0.5f * cosf((float)(2.0 * M_PI * (double)n) / (float)(cfg->nfft - 1));
-    CRN_CUDA(cudaMalloc(&h->d_win, sizeof(float) * w.size()));
-    CRN_CUDA(cudaMemcpy(h->d_win, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+    std::vector<float2> wp;
+    build_window_pairs(crn::radix_plan(cfg->nfft), wp);
+    CRN_CUDA(cudaMalloc(&h->d_win, sizeof(float2) * wp.size()));
+    CRN_CUDA(cudaMemcpy(h->d_win, wp.data(), sizeof(float2) * wp.size(), cudaMemcpyHostToDevice));
   }
 
   crn::SenseParams &b = h->base;
   memset(&b, 0, sizeof(b));
   b.tw = h->d_tw;
-  b.win = h->d_win;
+  b.winp = h->d_win;
+  b.upg = 1;
   b.L = cfg->frame_len;
   b.stride = h->stride;
   b.K = cfg->navg;
@@ -244,6 +278,7 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     crn_destroy(h);
     return crn::fail(CRN_ERR_CUDA, "kernel %s does not fit on an SM (smem %d B)", h->geo.name, h->geo.smem_bytes);
   }
+  b.upg = pick_upg(h->geo.units, h->geo.teams_per_unit, cfg->navg);
 
   CRN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CRN_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));

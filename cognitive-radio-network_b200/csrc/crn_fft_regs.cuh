@@ -107,10 +107,12 @@ __device__ __forceinline__ void butterfly(float2 &a, float2 &b) {
 }
 
 // In-place radix-R FFT.  On entry v[i] = x[bitrev(i)], on exit v[k] = X[k].
-template <int R>
+// FIRST = 1 runs all log2(R) stages; FIRST = 2 skips the first (span-2, twiddle-free) stage because the
+// caller has already done it, fused with a per-input weight (window or inter-pass twiddle).
+template <int R, int FIRST = 1>
 __device__ __forceinline__ void fft_dit(float2 (&v)[R]) {
   constexpr int LOG = ilog2(R);
-  static_for<1, LOG + 1>([&](auto S) {
+  static_for<FIRST, LOG + 1>([&](auto S) {
     constexpr int m = 1 << S.value;
     constexpr int h = m >> 1;
     static_for<0, R / m>([&](auto B) {
@@ -120,6 +122,30 @@ __device__ __forceinline__ void fft_dit(float2 (&v)[R]) {
       });
     });
   });
+}
+
+// First-stage butterfly fused with REAL input weights (window):  (p, q) = (wa a + wb b, wa a - wb b)
+// 2 FMUL + 4 FFMA instead of 4 FMUL + 4 FADD.
+__device__ __forceinline__ void butterfly_w_real(float2 a, float2 b, float wa, float wb, float2 &p, float2 &q) {
+  const float ax = wa * a.x, ay = wa * a.y;
+  p = make_float2(fmaf(wb, b.x, ax), fmaf(wb, b.y, ay));
+  q = make_float2(fmaf(2.0f, ax, -p.x), fmaf(2.0f, ay, -p.y));
+}
+// ... with COMPLEX input weights (inter-pass twiddles): 2 FMUL + 8 FFMA instead of 4 FMUL + 4 FFMA + 4 FADD
+// (A_IS_ONE: wa == 1, the q = 0 input of a Stockham pass: 6 FFMA).
+template <bool A_IS_ONE>
+__device__ __forceinline__ void butterfly_w_cplx(float2 a, float2 b, float2 wa, float2 wb, float2 &p, float2 &q) {
+  float ax = a.x, ay = a.y;
+  if constexpr (!A_IS_ONE) {
+    ax = fmaf(a.x, wa.x, -a.y * wa.y);
+    ay = fmaf(a.x, wa.y, a.y * wa.x);
+  }
+  float px = fmaf(b.x, wb.x, ax);
+  px = fmaf(-b.y, wb.y, px);
+  float py = fmaf(b.x, wb.y, ay);
+  py = fmaf(b.y, wb.x, py);
+  p = make_float2(px, py);
+  q = make_float2(fmaf(2.0f, ax, -px), fmaf(2.0f, ay, -py));
 }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {

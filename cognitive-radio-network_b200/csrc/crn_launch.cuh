@@ -14,6 +14,7 @@ struct LaunchGeometry {
   int smem_bytes;
   int regs;
   int threads_per_cta, threads_per_frame, elems_per_thread, teams;
+  int units, teams_per_unit;  // reduction units per CTA, teams per unit (see crn_sense_kernel.cuh)
   char name[64];
 };
 
@@ -41,6 +42,8 @@ int launch_one(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeom
     geo->threads_per_frame = P::T;
     geo->elems_per_thread = P::E;
     geo->teams = P::TEAMS;
+    geo->units = P::UNITS;
+    geo->teams_per_unit = P::TEAMS_PER_UNIT;
     snprintf(geo->name, sizeof(geo->name), "sense_n%d_r%dx%dx%d_%s_%s", P::N, P::R0, P::R1, P::R2,
              WIN ? "hann" : "rect", DET == DET_MAGSQ ? "magsq" : "mag");
     return CRN_OK;
@@ -70,17 +73,18 @@ int launch_sense_2048(const SenseParams &, int, int, int, cudaStream_t, LaunchGe
 int launch_sense_4096(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
 int launch_sense_8192(const SenseParams &, int, int, int, cudaStream_t, LaunchGeometry *);
 
-// Radix plan per size, needed by the host to build the twiddle tables.
-struct RadixPlan { int n, r0, r1, r2; };
+// Radix plan per size (must match the Plan<> in crn_sense_n<N>.cu): the host builds the paired twiddle
+// and window tables from it.
+struct RadixPlan { int n, e, r0, r1, r2; };
 inline RadixPlan radix_plan(int n) {
   switch (n) {
-    case 256: return {256, 16, 16, 1};
-    case 512: return {512, 32, 16, 1};
-    case 1024: return {1024, 32, 32, 1};
-    case 2048: return {2048, 32, 8, 8};
-    case 4096: return {4096, 16, 16, 16};
-    case 8192: return {8192, 32, 16, 16};
-    default: return {0, 0, 0, 0};
+    case 256: return {256, 16, 16, 16, 1};
+    case 512: return {512, 32, 32, 16, 1};
+    case 1024: return {1024, 32, 32, 32, 1};
+    case 2048: return {2048, 32, 32, 8, 8};
+    case 4096: return {4096, 16, 16, 16, 16};
+    case 8192: return {8192, 32, 32, 16, 16};
+    default: return {0, 0, 0, 0, 0};
   }
 }
 

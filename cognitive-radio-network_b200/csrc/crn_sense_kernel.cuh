@@ -3,7 +3,7 @@
 // One launch does, for every decision group (K frames of L <= N samples), what the reference engine
 // does across K calls of CE_Predictive_Node::execute():
 //     .cpp:149      stage L samples, zero tail                  -> predicated 8-byte global loads
-//     (extension)   window multiply                             -> smem table, fused into the load
+//     (extension)   window multiply                             -> folded into the first butterfly stage
 //     .cpp:150      fft_execute (N-point forward FFT)           -> register radix-16/32 passes with at
 //                                                                  most two shared-memory exchanges
 //     .cpp:152-154  fft_avg[i] += |X[i]| / K   (or |X[i]|^2)    -> per-thread register accumulators
@@ -19,6 +19,16 @@
 // the points {t + T*m, m = 0..E-1}: the first pass therefore reads global memory fully coalesced
 // (consecutive lanes -> consecutive samples), every exchange reads shared memory at unit stride, and
 // the last pass leaves bin (t + T*m) in register m, so the K-frame accumulators never leave registers.
+// The two inputs of every first-stage butterfly are registers (m, m + E/2), whatever the radix, so the
+// per-input weights (window in pass 0, inter-pass twiddles later) are stored as pairs and folded into
+// that stage.
+//
+// Work distribution.  A CTA is NT threads = UNITS reduction units (a unit is a warp, or a whole team
+// when a team spans several warps).  `upg` units share one decision group (its K frames are dealt
+// round-robin to their teams), so a CTA works on UNITS/upg groups at a time.  There is no CTA-wide
+// barrier in the steady state: each unit reduces its own accumulators to per-segment partial sums, and
+// the last unit of a group to arrive (shared-memory counter) combines them, runs the MLP and writes the
+// decision while the others already work on their next group.
 #pragma once
 #include <cstdint>
 
@@ -31,8 +41,8 @@ enum { DET_MAG = 0, DET_MAGSQ = 1 };
 
 struct SenseParams {
   const float2 *iq;      // [ngroups][K][stride] complex-float
-  const float2 *tw;      // inter-pass twiddles: pass-1 table then pass-2 table
-  const float *win;      // [N] window (nullptr for rectangular)
+  const float4 *tw;      // paired inter-pass twiddles: pass-1 table then pass-2 table
+  const float2 *winp;    // [N/2] paired window (nullptr for rectangular)
   float *feat;           // [ngroups][nbands]
   double *ann;           // [ngroups][3] or nullptr
   int32_t *decision;     // [ngroups] or nullptr
@@ -41,6 +51,7 @@ struct SenseParams {
   int L, stride, K;
   float invK;
   int nbands, nsegs, postop, decide;
+  int upg;               // reduction units per decision group (divides UNITS)
   double threshold, energy_factor;
   double wih[CRN_ANN_INPUTS + 1][CRN_ANN_HIDDEN + 1];
   double who[CRN_ANN_HIDDEN + 1][CRN_ANN_OUTPUTS + 1];
@@ -54,17 +65,26 @@ struct Plan {
   static constexpr int T = N / E;                  // threads per frame
   static constexpr int NT = T * TEAMS;             // threads per CTA
   static constexpr int PASSES = (R2 > 1) ? 3 : 2;
-  static constexpr int PADSHIFT = ilog2(R0);       // one pad slot per R0 points: conflict-free exchange
-  static constexpr int XSZ = N + (N >> PADSHIFT);  // float2 slots per team exchange buffer
-  static constexpr int TW1 = R0 * R1;              // pass-1 twiddle table entries
-  static constexpr int TW2 = (R2 > 1) ? N : 0;     // pass-2 twiddle table entries
+  static constexpr int PADSHIFT = ilog2(R0);       // two pad slots per R0 points: conflict-free, 16 B rows
+  static constexpr int XSZ = N + 2 * (N >> PADSHIFT);  // float2 slots per team exchange buffer
+  static constexpr int TW1 = R0 * R1 / 2;          // pass-1 paired twiddle table entries (float4)
+  static constexpr int TW2 = (R2 > 1) ? N / 2 : 0; // pass-2 paired twiddle table entries (float4)
+  static constexpr int UNIT_THREADS = T > 32 ? T : 32;
+  static constexpr int UNITS = NT / UNIT_THREADS;  // reduction units per CTA
+  static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
+#ifdef CRN_NO_PREFETCH
+  static constexpr bool PREFETCH = false;
+#else
+  static constexpr bool PREFETCH = true;           // software L2 prefetch one frame ahead
+#endif
   static_assert(R0 * R1 * R2 == N, "radices must multiply to N");
   static_assert(E % R0 == 0 && E % R1 == 0 && E % R2 == 0, "E must be a multiple of every radix");
   static_assert(R0 >= 16, "first radix < 16 would bank-conflict the exchange");
   static_assert(T >= 16 && (T <= 32 ? 32 % T == 0 : T % 32 == 0), "team must tile a warp");
+  static_assert(NT % UNIT_THREADS == 0 && UNITS <= 15, "units must tile the CTA (named barriers 1..15)");
   static constexpr size_t smem_bytes(bool win) {
-    return sizeof(float2) * ((size_t)TEAMS * XSZ + TW1 + TW2) + (win ? sizeof(float) * N : 0) +
-           sizeof(float) * (CRN_MAX_SEGS + CRN_MAX_BANDS);
+    return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win ? N / 2 : 0)) +
+           sizeof(float) * (2 * UNITS * CRN_MAX_SEGS + CRN_MAX_BANDS * UNITS) + sizeof(int) * 4 * UNITS;
   }
 };
 
@@ -72,6 +92,18 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p) {
   float2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
+}
+
+// Pull one frame (E*T*8 bytes, 128-byte lines) towards L2 ahead of use: lane t touches lines t + T*i.
+template <int E, int T>
+__device__ __forceinline__ void prefetch_frame_l2(const float2 *frame, int t, int frame_bytes) {
+  constexpr int LINES_PER_THREAD = (E + 15) / 16;  // E*T*8/128 lines over T threads
+#pragma unroll
+  for (int i = 0; i < LINES_PER_THREAD; i++) {
+    const int off = 128 * (t + T * i);
+    if (off < frame_bytes)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(frame) + off));
+  }
 }
 
 template <int T>
@@ -87,34 +119,61 @@ __device__ __forceinline__ void team_sync(int team) {
   }
 }
 
-// One radix-R pass over the E register-resident points: E/R independent FFTs, FFT #i on registers
-// {i + r*(E/R)}.
-template <int E, int R>
-__device__ __forceinline__ void reg_pass(float2 (&a)[E]) {
+// Pass 0: E/R radix-R FFTs on registers {i + q*(E/R)}; the window (if any) rides on the first stage.
+template <int E, int R, int T, bool WIN>
+__device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__restrict__ winp, int t) {
   constexpr int G = E / R;
   constexpr int LOG = ilog2(R);
   static_for<0, G>([&](auto I) {
     float2 v[R];
-    static_for<0, R>([&](auto Q) {
-      constexpr int br = bitrev(Q.value, LOG);
-      v[br] = a[I.value + Q.value * G];
+    static_for<0, R / 2>([&](auto Q) {
+      constexpr int m0 = I.value + Q.value * G;  // partner is register m0 + E/2
+      constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
+      if constexpr (WIN) {
+        const float2 w = winp[m0 * T + t];
+        butterfly_w_real(a[m0], a[m0 + E / 2], w.x, w.y, v[br], v[br + 1]);
+      } else {
+        v[br] = make_float2(a[m0].x + a[m0 + E / 2].x, a[m0].y + a[m0 + E / 2].y);
+        v[br + 1] = make_float2(a[m0].x - a[m0 + E / 2].x, a[m0].y - a[m0 + E / 2].y);
+      }
     });
-    fft_dit<R>(v);
+    fft_dit<R, 2>(v);
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
 }
 
-// Multiply by the inter-pass twiddles W_{Ns*R}^{r*(j mod Ns)}, j = t + T*i.
+// Pass p >= 1: inter-pass twiddles W_{Ns*R}^{q*(j mod Ns)}, j = t + T*i, folded into the first stage.
+// twp[q0*NS + (j mod NS)] = {W(q0), W(q0 + R/2)}.
 template <int E, int R, int T, int NS>
-__device__ __forceinline__ void apply_twiddles(float2 (&a)[E], const float2 *__restrict__ tw, int t) {
+__device__ __forceinline__ void reg_pass_tw(float2 (&a)[E], const float4 *__restrict__ twp, int t) {
   constexpr int G = E / R;
+  constexpr int LOG = ilog2(R);
   static_for<0, G>([&](auto I) {
-    const int q = (t + T * I.value) & (NS - 1);
-    static_for<1, R>([&](auto Q) {
-      const float2 w = tw[Q.value * NS + q];
-      a[I.value + Q.value * G] = cmul(a[I.value + Q.value * G], w);
+    const int jq = (t + T * I.value) & (NS - 1);
+    float2 v[R];
+    static_for<0, R / 2>([&](auto Q) {
+      constexpr int m0 = I.value + Q.value * G;
+      constexpr int br = bitrev(Q.value, LOG);
+#ifdef CRN_DEBUG_NO_TW
+      const float4 w = make_float4(0.6f, 0.8f, 0.8f, -0.6f + 1e-9f * jq);  // timing experiment only
+#elif defined(CRN_TW64)
+      const float2 *twp2 = reinterpret_cast<const float2 *>(twp + Q.value * NS + jq);
+      const float2 wlo = twp2[0], whi = twp2[1];
+      const float4 w = make_float4(wlo.x, wlo.y, whi.x, whi.y);
+#else
+      const float4 w = twp[Q.value * NS + jq];
+#endif
+      butterfly_w_cplx<Q.value == 0>(a[m0], a[m0 + E / 2], make_float2(w.x, w.y), make_float2(w.z, w.w),
+                                     v[br], v[br + 1]);
     });
+    fft_dit<R, 2>(v);
+    static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
+}
+
+template <int PADSHIFT>
+__device__ __forceinline__ int xphys(int idx) {
+  return idx + 2 * (idx >> PADSHIFT);
 }
 
 // Scatter the outputs of a radix-R pass (Ns = product of earlier radices) into the exchange buffer,
@@ -125,53 +184,89 @@ __device__ __forceinline__ void exchange(float2 (&a)[E], float2 *__restrict__ xb
   team_sync<T>(team);  // previous readers of xb are done
   static_for<0, G>([&](auto I) {
     const int j = t + T * I.value;
-    const int base = (j / NS) * (NS * R) + (j & (NS - 1));
-    static_for<0, R>([&](auto Q) {
-      const int idx = base + Q.value * NS;
-      xb[idx + (idx >> PADSHIFT)] = a[I.value + Q.value * G];
-    });
+#ifdef CRN_X64
+    if constexpr (false) {
+#else
+    if constexpr (NS == 1 && R == (1 << PADSHIFT)) {
+#endif
+      // pass 0: this thread owns one padded row of R consecutive points -> 16-byte stores
+      float4 *row = reinterpret_cast<float4 *>(xb + j * (R + 2));
+      static_for<0, R / 2>([&](auto Q) {
+        const float2 lo = a[I.value + (2 * Q.value) * G], hi = a[I.value + (2 * Q.value + 1) * G];
+        row[Q.value] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      });
+    } else {
+      const int base = (j / NS) * (NS * R) + (j & (NS - 1));
+      static_for<0, R>([&](auto Q) { xb[xphys<PADSHIFT>(base + Q.value * NS)] = a[I.value + Q.value * G]; });
+    }
   });
   team_sync<T>(team);
-  static_for<0, E>([&](auto M) {
-    const int idx = t + T * M.value;
-    a[M.value] = xb[idx + (idx >> PADSHIFT)];
-  });
+  static_for<0, E>([&](auto M) { a[M.value] = xb[xphys<PADSHIFT>(t + T * M.value)]; });
+}
+
+template <int T, int UT>
+__device__ __forceinline__ void unit_sync(int unit) {
+  if constexpr (T > 32) asm volatile("bar.sync %0, %1;" ::"r"(unit + 1), "r"(UT) : "memory");
+  else __syncwarp();
 }
 
 template <class P, bool WIN, int DET>
 __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams prm) {
   constexpr int N = P::N, E = P::E, T = P::T, TEAMS = P::TEAMS, NT = P::NT;
+  constexpr int UT = P::UNIT_THREADS, UNITS = P::UNITS, TPU = P::TEAMS_PER_UNIT;
+  constexpr bool PREFETCH = P::PREFETCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *xbuf = reinterpret_cast<float2 *>(smem_raw);
-  float2 *tw1 = xbuf + (size_t)TEAMS * P::XSZ;
-  float2 *tw2 = tw1 + P::TW1;
-  float *fl = reinterpret_cast<float *>(tw2 + P::TW2);
-  float *win = fl;
-  float *segsum = fl + (WIN ? N : 0);
-  float *featbuf = segsum + CRN_MAX_SEGS;
+  float4 *tw1 = reinterpret_cast<float4 *>(smem_raw);
+  float4 *tw2 = tw1 + P::TW1;
+  float2 *xbuf = reinterpret_cast<float2 *>(tw2 + P::TW2);
+  float2 *winp = xbuf + (size_t)TEAMS * P::XSZ;
+  float *segpart = reinterpret_cast<float *>(winp + (WIN ? N / 2 : 0));  // [2][UNITS][CRN_MAX_SEGS]
+  float *featbuf = segpart + 2 * UNITS * CRN_MAX_SEGS;                    // [UNITS][CRN_MAX_BANDS]
+  int *cnt = reinterpret_cast<int *>(featbuf + UNITS * CRN_MAX_BANDS);    // [2][UNITS] arrivals
+  volatile int *done = cnt + 2 * UNITS;                                   // [2][UNITS] completed combines
 
   const int tid = threadIdx.x;
   const int team = tid / T;
   const int t = tid % T;
+  const int unit = tid / UT;            // reduction unit of this thread
+  const int ut = tid % UT;              // thread index inside the unit
+  const int upg = prm.upg;
+  const int GL = UNITS / upg;           // decision groups in flight per CTA
+  const int gl = unit / upg;            // which of them this unit works on
+  const int fs = (unit % upg) * TPU + (ut / T);  // this team's frame slot inside the group
+  const int FT = upg * TPU;             // teams per group
   float2 *xb = xbuf + (size_t)team * P::XSZ;
+  float *part = reinterpret_cast<float *>(xbuf + (size_t)(unit * TPU) * P::XSZ);  // unit's N floats
 
   // one-time table staging (persistent CTA: amortised over all its groups)
   for (int i = tid; i < P::TW1 + P::TW2; i += NT) tw1[i] = prm.tw[i];
   if constexpr (WIN)
-    for (int i = tid; i < N; i += NT) win[i] = prm.win[i];
+    for (int i = tid; i < N / 2; i += NT) winp[i] = prm.winp[i];
+  for (int i = tid; i < 4 * UNITS; i += NT) cnt[i] = 0;
   __syncthreads();
 
   const int L = prm.L, K = prm.K;
   const bool full = (L == N);
+  const long long gstep = (long long)gridDim.x * GL;
 
-  for (long long g = blockIdx.x; g < prm.ngroups; g += gridDim.x) {
+  int it = 0;
+  for (long long g = (long long)blockIdx.x * GL + gl; g < prm.ngroups; g += gstep, it++) {
     float acc[E];
 #pragma unroll
     for (int m = 0; m < E; m++) acc[m] = 0.0f;
 
     const float2 *gbase = prm.iq + (size_t)g * (size_t)K * (size_t)prm.stride;
-    for (int k = team; k < K; k += TEAMS) {
+    for (int k = fs; k < K; k += FT) {
       const float2 *x = gbase + (size_t)k * (size_t)prm.stride + t;
+      if constexpr (PREFETCH) {
+        // the frame this team senses next: k + FT of this group, else its first frame of the next
+        // group.  One frame of compute covers the DRAM latency, so the loads below hit L2.
+        const float2 *nx = nullptr;
+        if (k + FT < K) nx = x - t + (size_t)FT * (size_t)prm.stride;
+        else if (g + gstep < prm.ngroups)
+          nx = prm.iq + ((size_t)(g + gstep) * (size_t)K + (size_t)fs) * (size_t)prm.stride;
+        if (nx) prefetch_frame_l2<E, T>(nx, t, L * 8);
+      }
       float2 a[E];
       if (full) {
 #pragma unroll
@@ -180,24 +275,14 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
 #pragma unroll
         for (int m = 0; m < E; m++) a[m] = (t + T * m < L) ? ld_stream(x + T * m) : make_float2(0.f, 0.f);
       }
-      if constexpr (WIN) {
-#pragma unroll
-        for (int m = 0; m < E; m++) {
-          const float w = win[t + T * m];
-          a[m].x *= w;
-          a[m].y *= w;
-        }
-      }
-      // pass 0 (no twiddles: Ns = 1)
-      reg_pass<E, P::R0>(a);
+      // pass 0 (Ns = 1: no twiddles; window folded in)
+      reg_pass_first<E, P::R0, T, WIN>(a, winp, t);
       exchange<E, P::R0, T, 1, P::PADSHIFT>(a, xb, t, team);
       // pass 1
-      apply_twiddles<E, P::R1, T, P::R0>(a, tw1, t);
-      reg_pass<E, P::R1>(a);
+      reg_pass_tw<E, P::R1, T, P::R0>(a, tw1, t);
       if constexpr (P::PASSES == 3) {
         exchange<E, P::R1, T, P::R0, P::PADSHIFT>(a, xb, t, team);
-        apply_twiddles<E, P::R2, T, P::R0 * P::R1>(a, tw2, t);
-        reg_pass<E, P::R2>(a);
+        reg_pass_tw<E, P::R2, T, P::R0 * P::R1>(a, tw2, t);
       }
       // register m now holds bin t + T*m  (.cpp:152-154)
 #pragma unroll
@@ -213,98 +298,126 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       }
     }
 
-    // ---- per-group epilogue: band sums, features, MLP, decision ------------------------------------
-    __syncthreads();  // every team finished reading its exchange buffer
-    {
-      float *part = reinterpret_cast<float *>(xb);  // N floats per team, aliasing the exchange buffer
+    // ---- per-group epilogue -------------------------------------------------------------------------
+    // (1) unit-local: accumulators -> shared (aliasing the unit's own exchange buffer) -> per-segment
+    //     partial sums.  Only the unit's own threads synchronise.
+    const int slot = it & 1;
+    if constexpr (TPU == 2) {  // two half-warp teams hold the same bins: fold them first
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < E; m++) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 16);
+    }
+    unit_sync<T, UT>(unit);  // every thread of the unit is done reading its exchange buffer
+    if (ut < T) {
 #pragma unroll
       for (int m = 0; m < E; m++) part[t + T * m] = acc[m];
     }
-    __syncthreads();
+    unit_sync<T, UT>(unit);
     {
-      const int warp = tid >> 5, lane = tid & 31;
-      constexpr int NW = NT / 32;
-      for (int s = warp; s < prm.nsegs; s += NW) {
-        float sum = 0.0f;
-        for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) {
-#pragma unroll
-          for (int q = 0; q < TEAMS; q++) sum += reinterpret_cast<const float *>(xbuf + (size_t)q * P::XSZ)[i];
+      const int wu = ut >> 5, lane = tid & 31;
+      constexpr int NWU = UT / 32;
+      // ring guard: the combine that last used this slot (two groups ago) must have finished reading
+      if (lane == 0) {
+        while (done[slot * UNITS + gl] != (it >> 1)) {
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) segsum[s] = sum;
-      }
-    }
-    __syncthreads();
-    if (tid < 32) {
-      const int lane = tid;
-      for (int b = lane; b < prm.nbands; b += 32) {
-        float m = 0.0f;
-        for (int s = 0; s < prm.nsegs; s++)
-          if (prm.seg_band[s] == b) m += segsum[s];
-        m *= prm.invK;
-        const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
-        featbuf[b] = f;
-        prm.feat[(size_t)g * prm.nbands + b] = f;
       }
       __syncwarp();
-      if (prm.decide == CRN_DECIDE_ANN) {
-        if (lane == 0) {
-          // .cpp:200,214-235: double-precision 4-5-3 logistic MLP, bias at index 0
-          double H[CRN_ANN_HIDDEN + 1];
+      float *mine = segpart + ((size_t)slot * UNITS + unit) * CRN_MAX_SEGS;
+      for (int s = wu; s < prm.nsegs; s += NWU) {
+        float sum = 0.0f;
+        for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) sum += part[i];
 #pragma unroll
-          for (int j = 1; j <= CRN_ANN_HIDDEN; j++) {
-            double sum = prm.wih[0][j];
-#pragma unroll
-            for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += (double)featbuf[i - 1] * prm.wih[i][j];
-            H[j] = 1.0 / (1.0 + exp(-sum));
-          }
-          double out[CRN_ANN_OUTPUTS + 1];
-#pragma unroll
-          for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) {
-            double sum = prm.who[0][k];
-#pragma unroll
-            for (int j = 1; j <= CRN_ANN_HIDDEN; j++) sum += H[j] * prm.who[j][k];
-            out[k] = 1.0 / (1.0 + exp(-sum));
-          }
-          int dec = CRN_ALL_BUSY;  // .cpp:245-261
-          if (out[1] >= prm.threshold) dec = CRN_CH1_OCCUPIED;
-          else if (out[2] >= prm.threshold) dec = CRN_CH2_OCCUPIED;
-          else if (out[3] >= prm.threshold) dec = CRN_CH3_OCCUPIED;
-          if (prm.ann) {
-            prm.ann[3 * g + 0] = out[1];
-            prm.ann[3 * g + 1] = out[2];
-            prm.ann[3 * g + 2] = out[3];
-          }
-          if (prm.decision) prm.decision[g] = dec;
-          if (prm.mask) prm.mask[g] = dec ? (1ull << (dec - 1)) : 0ull;
-        }
-      } else {
-        unsigned long long msk = 0ull;
-        if (prm.decide == CRN_DECIDE_ENERGY) {
-          float mn = 3.4e38f;
-          for (int b = lane; b < prm.nbands; b += 32) mn = fminf(mn, featbuf[b]);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-          for (int b = lane; b < prm.nbands; b += 32)
-            if ((double)featbuf[b] > prm.energy_factor * (double)mn) msk |= (1ull << b);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) msk |= __shfl_xor_sync(0xffffffffu, msk, o);
-        }
-        if (lane == 0) {
-          if (prm.ann) {
-            prm.ann[3 * g + 0] = 0.0;
-            prm.ann[3 * g + 1] = 0.0;
-            prm.ann[3 * g + 2] = 0.0;
-          }
-          if (prm.decision) prm.decision[g] = 0;
-          if (prm.mask) prm.mask[g] = msk;
-        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) mine[s] = sum;
       }
     }
-    // The next group's first exchange starts with a team_sync, but other warps may still be reading
-    // `part` in the band reduction of THIS group only before the barrier above - nothing after it
-    // reads the exchange buffers, so no further barrier is needed here.
+    unit_sync<T, UT>(unit);  // partial sums written, `part` free again
+
+    // (2) the unit's first warp announces arrival; the last unit of the group combines and decides
+    if (ut < 32) {
+      const int lane = ut;
+      int last = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        last = (atomicAdd(&cnt[slot * UNITS + gl], 1) == upg - 1);
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence_block();
+        float *fb = featbuf + unit * CRN_MAX_BANDS;
+        const float *sp = segpart + ((size_t)slot * UNITS + (size_t)gl * upg) * CRN_MAX_SEGS;
+        for (int b = lane; b < prm.nbands; b += 32) {
+          float m = 0.0f;
+          for (int s = 0; s < prm.nsegs; s++)
+            if (prm.seg_band[s] == b)
+              for (int u = 0; u < upg; u++) m += sp[u * CRN_MAX_SEGS + s];
+          m *= prm.invK;
+          const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
+          fb[b] = f;
+          prm.feat[(size_t)g * prm.nbands + b] = f;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          cnt[slot * UNITS + gl] = 0;
+          __threadfence_block();
+          done[slot * UNITS + gl] = (it >> 1) + 1;  // partial sums consumed: the slot may be reused
+        }
+        if (prm.decide == CRN_DECIDE_ANN) {
+          if (lane == 0) {
+            // .cpp:200,214-235: double-precision 4-5-3 logistic MLP, bias at index 0
+            double H[CRN_ANN_HIDDEN + 1];
+#pragma unroll
+            for (int j = 1; j <= CRN_ANN_HIDDEN; j++) {
+              double sum = prm.wih[0][j];
+#pragma unroll
+              for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += (double)fb[i - 1] * prm.wih[i][j];
+              H[j] = 1.0 / (1.0 + exp(-sum));
+            }
+            double out[CRN_ANN_OUTPUTS + 1];
+#pragma unroll
+            for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) {
+              double sum = prm.who[0][k];
+#pragma unroll
+              for (int j = 1; j <= CRN_ANN_HIDDEN; j++) sum += H[j] * prm.who[j][k];
+              out[k] = 1.0 / (1.0 + exp(-sum));
+            }
+            int dec = CRN_ALL_BUSY;  // .cpp:245-261
+            if (out[1] >= prm.threshold) dec = CRN_CH1_OCCUPIED;
+            else if (out[2] >= prm.threshold) dec = CRN_CH2_OCCUPIED;
+            else if (out[3] >= prm.threshold) dec = CRN_CH3_OCCUPIED;
+            if (prm.ann) {
+              prm.ann[3 * g + 0] = out[1];
+              prm.ann[3 * g + 1] = out[2];
+              prm.ann[3 * g + 2] = out[3];
+            }
+            if (prm.decision) prm.decision[g] = dec;
+            if (prm.mask) prm.mask[g] = dec ? (1ull << (dec - 1)) : 0ull;
+          }
+        } else {
+          unsigned long long msk = 0ull;
+          if (prm.decide == CRN_DECIDE_ENERGY) {
+            float mn = 3.4e38f;
+            for (int b = lane; b < prm.nbands; b += 32) mn = fminf(mn, fb[b]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            for (int b = lane; b < prm.nbands; b += 32)
+              if ((double)fb[b] > prm.energy_factor * (double)mn) msk |= (1ull << b);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) msk |= __shfl_xor_sync(0xffffffffu, msk, o);
+          }
+          if (lane == 0) {
+            if (prm.ann) {
+              prm.ann[3 * g + 0] = 0.0;
+              prm.ann[3 * g + 1] = 0.0;
+              prm.ann[3 * g + 2] = 0.0;
+            }
+            if (prm.decision) prm.decision[g] = 0;
+            if (prm.mask) prm.mask[g] = msk;
+          }
+        }
+        __syncwarp();  // fb is reused by this warp's next combine
+      }
+    }
   }
 }
 
