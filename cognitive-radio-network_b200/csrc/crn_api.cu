@@ -166,7 +166,7 @@ int pick_upg(int units, int teams_per_unit, int K) {
 
 int grid_for(const crn_handle *h, int64_t ngroups) {
   int64_t g = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
-  const int64_t gl = h->geo.units / h->base.upg;  // decision groups a CTA works on at a time
+  const int64_t gl = h->base.upg > 0 ? h->geo.units / h->base.upg : 1;  // groups a CTA works on at a time
   const int64_t need = (ngroups + gl - 1) / gl;
   if (need < g) g = need;
   return (int)(g < 1 ? 1 : g);
@@ -278,7 +278,19 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     crn_destroy(h);
     return crn::fail(CRN_ERR_CUDA, "kernel %s does not fit on an SM (smem %d B)", h->geo.name, h->geo.smem_bytes);
   }
-  b.upg = pick_upg(h->geo.units, h->geo.teams_per_unit, cfg->navg);
+  // Epilogue strategy (crn_sense_kernel.cuh): CTA-wide when every team gets the same, long run of frames
+  // per group; otherwise the barrier-free unit epilogue with the best-balanced units-per-group.
+  {
+    const int teams = h->geo.teams;
+    const bool long_even_groups = (cfg->navg % teams == 0) && (cfg->navg / teams >= 8);
+    const char *force = getenv("CRN_EPI");  // "cta" | "unit": development override
+    bool cta = long_even_groups;
+    if (force && !strcmp(force, "cta")) cta = true;
+    if (force && !strcmp(force, "unit")) cta = false;
+    b.upg = cta ? 0 : pick_upg(h->geo.units, h->geo.teams_per_unit, cfg->navg);
+    st = h->launch(b, cfg->window, cfg->detector, 0, nullptr, &h->geo);  // attributes of the chosen variant
+    if (st != CRN_OK) { crn_destroy(h); return st; }
+  }
 
   CRN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CRN_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));

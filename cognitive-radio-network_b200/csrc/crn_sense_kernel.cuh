@@ -81,7 +81,7 @@ struct Plan {
   static_assert(E % R0 == 0 && E % R1 == 0 && E % R2 == 0, "E must be a multiple of every radix");
   static_assert(R0 >= 16, "first radix < 16 would bank-conflict the exchange");
   static_assert(T >= 16 && (T <= 32 ? 32 % T == 0 : T % 32 == 0), "team must tile a warp");
-  static_assert(NT % UNIT_THREADS == 0 && UNITS <= 15, "units must tile the CTA (named barriers 1..15)");
+  static_assert(NT % UNIT_THREADS == 0 && (T <= 32 || UNITS <= 15), "units must tile the CTA (named barriers 1..15)");
   static constexpr size_t smem_bytes(bool win) {
     return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win ? N / 2 : 0)) +
            sizeof(float) * (2 * UNITS * CRN_MAX_SEGS + CRN_MAX_BANDS * UNITS) + sizeof(int) * 4 * UNITS;
@@ -95,14 +95,14 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p) {
 }
 
 // Pull one frame (E*T*8 bytes, 128-byte lines) towards L2 ahead of use: lane t touches lines t + T*i.
+// `line` points at this thread's first line (frame + 128 t bytes); `bytes_left` = frame bytes beyond it.
 template <int E, int T>
-__device__ __forceinline__ void prefetch_frame_l2(const float2 *frame, int t, int frame_bytes) {
+__device__ __forceinline__ void prefetch_frame_l2(const float2 *line, int bytes_left) {
   constexpr int LINES_PER_THREAD = (E + 15) / 16;  // E*T*8/128 lines over T threads
 #pragma unroll
   for (int i = 0; i < LINES_PER_THREAD; i++) {
-    const int off = 128 * (t + T * i);
-    if (off < frame_bytes)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(frame) + off));
+    if (128 * T * i < bytes_left)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(line) + 128 * T * i));
   }
 }
 
@@ -131,7 +131,13 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
       constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
       if constexpr (WIN) {
         const float2 w = winp[m0 * T + t];
+#ifdef CRN_NOFUSE_WIN
+        const float2 A = make_float2(a[m0].x * w.x, a[m0].y * w.x), B = make_float2(a[m0 + E / 2].x * w.y, a[m0 + E / 2].y * w.y);
+        v[br] = make_float2(A.x + B.x, A.y + B.y);
+        v[br + 1] = make_float2(A.x - B.x, A.y - B.y);
+#else
         butterfly_w_real(a[m0], a[m0 + E / 2], w.x, w.y, v[br], v[br + 1]);
+#endif
       } else {
         v[br] = make_float2(a[m0].x + a[m0 + E / 2].x, a[m0].y + a[m0 + E / 2].y);
         v[br + 1] = make_float2(a[m0].x - a[m0 + E / 2].x, a[m0].y - a[m0 + E / 2].y);
@@ -163,17 +169,29 @@ __device__ __forceinline__ void reg_pass_tw(float2 (&a)[E], const float4 *__rest
 #else
       const float4 w = twp[Q.value * NS + jq];
 #endif
+#ifdef CRN_NOFUSE_TW
+      const float2 A = (Q.value == 0) ? a[m0] : cmul(a[m0], make_float2(w.x, w.y));
+      const float2 B = cmul(a[m0 + E / 2], make_float2(w.z, w.w));
+      v[br] = make_float2(A.x + B.x, A.y + B.y);
+      v[br + 1] = make_float2(A.x - B.x, A.y - B.y);
+#else
       butterfly_w_cplx<Q.value == 0>(a[m0], a[m0 + E / 2], make_float2(w.x, w.y), make_float2(w.z, w.w),
                                      v[br], v[br + 1]);
+#endif
     });
     fft_dit<R, 2>(v);
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
 }
 
+#ifdef CRN_X64
+#define CRN_XPAD 1  // 8-byte exchange stores: one pad slot per row is conflict-free
+#else
+#define CRN_XPAD 2  // 16-byte exchange stores need 16-byte aligned rows
+#endif
 template <int PADSHIFT>
 __device__ __forceinline__ int xphys(int idx) {
-  return idx + 2 * (idx >> PADSHIFT);
+  return idx + CRN_XPAD * (idx >> PADSHIFT);
 }
 
 // Scatter the outputs of a radix-R pass (Ns = product of earlier radices) into the exchange buffer,
@@ -190,7 +208,7 @@ __device__ __forceinline__ void exchange(float2 (&a)[E], float2 *__restrict__ xb
     if constexpr (NS == 1 && R == (1 << PADSHIFT)) {
 #endif
       // pass 0: this thread owns one padded row of R consecutive points -> 16-byte stores
-      float4 *row = reinterpret_cast<float4 *>(xb + j * (R + 2));
+      float4 *row = reinterpret_cast<float4 *>(xb + j * (R + CRN_XPAD));
       static_for<0, R / 2>([&](auto Q) {
         const float2 lo = a[I.value + (2 * Q.value) * G], hi = a[I.value + (2 * Q.value + 1) * G];
         row[Q.value] = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -210,7 +228,71 @@ __device__ __forceinline__ void unit_sync(int unit) {
   else __syncwarp();
 }
 
-template <class P, bool WIN, int DET>
+// MLP + first-match chain (or energy detector) for one decision, run by one warp; `fb` holds the features.
+__device__ __forceinline__ void decide_and_store(const SenseParams &prm, const float *fb, long long g, int lane) {
+  if (prm.decide == CRN_DECIDE_ANN) {
+    if (lane == 0) {
+      // .cpp:200,214-235: double-precision 4-5-3 logistic MLP, bias at index 0
+      double H[CRN_ANN_HIDDEN + 1];
+#pragma unroll
+      for (int j = 1; j <= CRN_ANN_HIDDEN; j++) {
+        double sum = prm.wih[0][j];
+#pragma unroll
+        for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += (double)fb[i - 1] * prm.wih[i][j];
+        H[j] = 1.0 / (1.0 + exp(-sum));
+      }
+      double out[CRN_ANN_OUTPUTS + 1];
+#pragma unroll
+      for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) {
+        double sum = prm.who[0][k];
+#pragma unroll
+        for (int j = 1; j <= CRN_ANN_HIDDEN; j++) sum += H[j] * prm.who[j][k];
+        out[k] = 1.0 / (1.0 + exp(-sum));
+      }
+      int dec = CRN_ALL_BUSY;  // .cpp:245-261
+      if (out[1] >= prm.threshold) dec = CRN_CH1_OCCUPIED;
+      else if (out[2] >= prm.threshold) dec = CRN_CH2_OCCUPIED;
+      else if (out[3] >= prm.threshold) dec = CRN_CH3_OCCUPIED;
+      if (prm.ann) {
+        prm.ann[3 * g + 0] = out[1];
+        prm.ann[3 * g + 1] = out[2];
+        prm.ann[3 * g + 2] = out[3];
+      }
+      if (prm.decision) prm.decision[g] = dec;
+      if (prm.mask) prm.mask[g] = dec ? (1ull << (dec - 1)) : 0ull;
+    }
+  } else {
+    unsigned long long msk = 0ull;
+    if (prm.decide == CRN_DECIDE_ENERGY) {
+      float mn = 3.4e38f;
+      for (int b = lane; b < prm.nbands; b += 32) mn = fminf(mn, fb[b]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      for (int b = lane; b < prm.nbands; b += 32)
+        if ((double)fb[b] > prm.energy_factor * (double)mn) msk |= (1ull << b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) msk |= __shfl_xor_sync(0xffffffffu, msk, o);
+    }
+    if (lane == 0) {
+      if (prm.ann) {
+        prm.ann[3 * g + 0] = 0.0;
+        prm.ann[3 * g + 1] = 0.0;
+        prm.ann[3 * g + 2] = 0.0;
+      }
+      if (prm.decision) prm.decision[g] = 0;
+      if (prm.mask) prm.mask[g] = msk;
+    }
+  }
+}
+
+// EPI selects how the teams of a CTA share decision groups:
+//   EPI_CTA  - the whole CTA works on one group (team q takes frames q, q+TEAMS, ...) and meets at three
+//              CTA barriers per group to reduce; cheapest per group, best when a group is long (K >> TEAMS).
+//   EPI_UNIT - `upg` units share a group and nobody waits: the last unit to arrive combines.  Keeps every
+//              warp busy when groups are short (reference mode: K = 10) or K does not divide by TEAMS.
+enum { EPI_CTA = 0, EPI_UNIT = 1 };
+
+template <class P, bool WIN, int DET, int EPI>
 __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams prm) {
   constexpr int N = P::N, E = P::E, T = P::T, TEAMS = P::TEAMS, NT = P::NT;
   constexpr int UT = P::UNIT_THREADS, UNITS = P::UNITS, TPU = P::TEAMS_PER_UNIT;
@@ -230,11 +312,11 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
   const int t = tid % T;
   const int unit = tid / UT;            // reduction unit of this thread
   const int ut = tid % UT;              // thread index inside the unit
-  const int upg = prm.upg;
-  const int GL = UNITS / upg;           // decision groups in flight per CTA
-  const int gl = unit / upg;            // which of them this unit works on
-  const int fs = (unit % upg) * TPU + (ut / T);  // this team's frame slot inside the group
-  const int FT = upg * TPU;             // teams per group
+  const int upg = (EPI == EPI_CTA) ? UNITS : prm.upg;
+  const int GL = (EPI == EPI_CTA) ? 1 : UNITS / upg;   // decision groups in flight per CTA
+  const int gl = (EPI == EPI_CTA) ? 0 : unit / upg;    // which of them this unit works on
+  const int fs = (EPI == EPI_CTA) ? team : (unit % upg) * TPU + (ut / T);  // frame slot inside the group
+  const int FT = (EPI == EPI_CTA) ? TEAMS : upg * TPU;  // teams per group
   float2 *xb = xbuf + (size_t)team * P::XSZ;
   float *part = reinterpret_cast<float *>(xbuf + (size_t)(unit * TPU) * P::XSZ);  // unit's N floats
 
@@ -251,21 +333,25 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
 
   int it = 0;
   for (long long g = (long long)blockIdx.x * GL + gl; g < prm.ngroups; g += gstep, it++) {
+#ifdef CRN_ALIGN_GROUPS
+    __syncthreads();  // experiment: re-align the CTA's warps at every group (valid when upg == UNITS)
+#endif
     float acc[E];
 #pragma unroll
     for (int m = 0; m < E; m++) acc[m] = 0.0f;
 
-    const float2 *gbase = prm.iq + (size_t)g * (size_t)K * (size_t)prm.stride;
-    for (int k = fs; k < K; k += FT) {
-      const float2 *x = gbase + (size_t)k * (size_t)prm.stride + t;
+    // frame pointers advance by plain 64-bit adds inside the loop; the multiplications happen once per group
+    const size_t fstep = (size_t)FT * (size_t)prm.stride;  // samples between this team's frames
+    const float2 *x = prm.iq + ((size_t)g * (size_t)K + (size_t)fs) * (size_t)prm.stride + t;
+    // first frame this team senses in the CTA's next group (prefetch target at the group boundary);
+    // "+ 15 t" turns the per-thread sample pointer into a per-thread 128-byte line pointer (16 samples/line)
+    const float2 *xng = (g + gstep < prm.ngroups) ? x + (size_t)gstep * (size_t)K * (size_t)prm.stride + 15 * t : nullptr;
+    for (int k = fs; k < K; k += FT, x += fstep) {
       if constexpr (PREFETCH) {
         // the frame this team senses next: k + FT of this group, else its first frame of the next
         // group.  One frame of compute covers the DRAM latency, so the loads below hit L2.
-        const float2 *nx = nullptr;
-        if (k + FT < K) nx = x - t + (size_t)FT * (size_t)prm.stride;
-        else if (g + gstep < prm.ngroups)
-          nx = prm.iq + ((size_t)(g + gstep) * (size_t)K + (size_t)fs) * (size_t)prm.stride;
-        if (nx) prefetch_frame_l2<E, T>(nx, t, L * 8);
+        const float2 *nx = (k + FT < K) ? x + fstep + 15 * t : xng;
+        if (nx) prefetch_frame_l2<E, T>(nx, L * 8 - 128 * t);
       }
       float2 a[E];
       if (full) {
@@ -298,6 +384,47 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       }
     }
 
+    if constexpr (EPI == EPI_CTA) {
+      // ---- per-group epilogue, CTA-wide ----------------------------------------------------------------
+      float *segsum = segpart;  // [CRN_MAX_SEGS]
+      __syncthreads();          // every team finished reading its exchange buffer
+      {
+        float *mypart = reinterpret_cast<float *>(xb);  // N floats per team, aliasing the exchange buffer
+#pragma unroll
+        for (int m = 0; m < E; m++) mypart[t + T * m] = acc[m];
+      }
+      __syncthreads();
+      {
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int NW = NT / 32;
+        for (int s = warp; s < prm.nsegs; s += NW) {
+          float sum = 0.0f;
+          for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) {
+#pragma unroll
+            for (int q = 0; q < TEAMS; q++) sum += reinterpret_cast<const float *>(xbuf + (size_t)q * P::XSZ)[i];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) segsum[s] = sum;
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {
+        for (int b = tid; b < prm.nbands; b += 32) {
+          float m = 0.0f;
+          for (int s = 0; s < prm.nsegs; s++)
+            if (prm.seg_band[s] == b) m += segsum[s];
+          m *= prm.invK;
+          const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
+          featbuf[b] = f;
+          prm.feat[(size_t)g * prm.nbands + b] = f;
+        }
+        __syncwarp();
+        decide_and_store(prm, featbuf, g, tid);
+      }
+      // nothing after the last barrier reads the exchange buffers, so the next group may start at once;
+      // segsum/featbuf are rewritten only after the next group's barriers.
+    } else {
     // ---- per-group epilogue -------------------------------------------------------------------------
     // (1) unit-local: accumulators -> shared (aliasing the unit's own exchange buffer) -> per-segment
     //     partial sums.  Only the unit's own threads synchronise.
@@ -362,61 +489,10 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
           __threadfence_block();
           done[slot * UNITS + gl] = (it >> 1) + 1;  // partial sums consumed: the slot may be reused
         }
-        if (prm.decide == CRN_DECIDE_ANN) {
-          if (lane == 0) {
-            // .cpp:200,214-235: double-precision 4-5-3 logistic MLP, bias at index 0
-            double H[CRN_ANN_HIDDEN + 1];
-#pragma unroll
-            for (int j = 1; j <= CRN_ANN_HIDDEN; j++) {
-              double sum = prm.wih[0][j];
-#pragma unroll
-              for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += (double)fb[i - 1] * prm.wih[i][j];
-              H[j] = 1.0 / (1.0 + exp(-sum));
-            }
-            double out[CRN_ANN_OUTPUTS + 1];
-#pragma unroll
-            for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) {
-              double sum = prm.who[0][k];
-#pragma unroll
-              for (int j = 1; j <= CRN_ANN_HIDDEN; j++) sum += H[j] * prm.who[j][k];
-              out[k] = 1.0 / (1.0 + exp(-sum));
-            }
-            int dec = CRN_ALL_BUSY;  // .cpp:245-261
-            if (out[1] >= prm.threshold) dec = CRN_CH1_OCCUPIED;
-            else if (out[2] >= prm.threshold) dec = CRN_CH2_OCCUPIED;
-            else if (out[3] >= prm.threshold) dec = CRN_CH3_OCCUPIED;
-            if (prm.ann) {
-              prm.ann[3 * g + 0] = out[1];
-              prm.ann[3 * g + 1] = out[2];
-              prm.ann[3 * g + 2] = out[3];
-            }
-            if (prm.decision) prm.decision[g] = dec;
-            if (prm.mask) prm.mask[g] = dec ? (1ull << (dec - 1)) : 0ull;
-          }
-        } else {
-          unsigned long long msk = 0ull;
-          if (prm.decide == CRN_DECIDE_ENERGY) {
-            float mn = 3.4e38f;
-            for (int b = lane; b < prm.nbands; b += 32) mn = fminf(mn, fb[b]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            for (int b = lane; b < prm.nbands; b += 32)
-              if ((double)fb[b] > prm.energy_factor * (double)mn) msk |= (1ull << b);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) msk |= __shfl_xor_sync(0xffffffffu, msk, o);
-          }
-          if (lane == 0) {
-            if (prm.ann) {
-              prm.ann[3 * g + 0] = 0.0;
-              prm.ann[3 * g + 1] = 0.0;
-              prm.ann[3 * g + 2] = 0.0;
-            }
-            if (prm.decision) prm.decision[g] = 0;
-            if (prm.mask) prm.mask[g] = msk;
-          }
-        }
+        decide_and_store(prm, fb, g, lane);
         __syncwarp();  // fb is reused by this warp's next combine
       }
+    }
     }
   }
 }
