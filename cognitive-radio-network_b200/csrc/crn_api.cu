@@ -182,6 +182,10 @@ int launch(crn_handle *h, const float2 *d_iq, int64_t ngroups, float *d_feat, do
   p.decision = d_dec;
   p.mask = d_mask;
   p.ngroups = ngroups;
+  // bulk-copy (TMA) staging needs 16-byte aligned frame addresses and sizes; anything else uses plain loads
+  const char *no_tma = getenv("CRN_NO_TMA");
+  p.use_tma = (p.upg == 0) && !(no_tma && no_tma[0] == '1') && ((reinterpret_cast<uintptr_t>(d_iq) & 15) == 0) &&
+              (h->stride % 2 == 0) && (h->cfg.frame_len % 2 == 0);
   int st = h->launch(p, h->cfg.window, h->cfg.detector, grid_for(h, ngroups), s, nullptr);
   if (st == CRN_OK) h->launches++;
   return st;
