@@ -67,49 +67,86 @@ def base_config(extra=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+    NVML is polled every 2 ms from a thread (the timed region is tens of milliseconds); falls back to
+    `nvidia-smi -lms` when the NVML binding is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # (time, sm_mhz, power_w, reason_bits)
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.max_mhz = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        getr = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.time(), float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)),
+                                  n.nvmlDeviceGetPowerUsage(self.h) / 1e3, int(getr(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 9:
+                bits = 0
+                for bit, v in zip((0x8, 0x40, 0x20, 0x4), r[5:9]):
+                    if v.lower().startswith("active"):
+                        bits |= bit
+                try:
+                    self.max_mhz = float(r[2])
+                    self.rows.append((time.time(), float(r[1]), float(r[3]), bits))
+                except ValueError:
+                    pass
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        inside = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        time.sleep(0.01)
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
         if not inside:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in inside)
-        reasons = set()
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        sm = sorted(r[1] for r in inside)
+        bits = 0
         for r in inside:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][2]), "samples": len(inside),
-                "power_w_max": max(float(r[3]) for r in inside), "reasons": sorted(reasons)}
+            bits |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "samples": len(inside),
+                "power_w_max": max(r[2] for r in inside),
+                "reasons": sorted(name for bit, name in self.REASONS.items() if bits & bit),
+                "source": "nvml 2 ms poll" if self.nvml else "nvidia-smi -lms 20"}
 
 
 def measured_peak():

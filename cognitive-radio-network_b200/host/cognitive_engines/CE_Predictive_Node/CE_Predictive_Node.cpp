@@ -169,5 +169,3 @@ void CE_Predictive_Node::execute() {
     }
   }
 }
-
-CRN_REGISTER_CE(CE_Predictive_Node)

@@ -19,13 +19,29 @@
 #ifndef CRN_HOST_ECR_HPP
 #define CRN_HOST_ECR_HPP
 
+// Upstream's header drags these in (through crts.hpp, liquid and UHD); engines written against it rely on
+// that, e.g. CE_Template.cpp uses getopt()/atoi() without including anything itself.
+#include <getopt.h>
+#include <math.h>
 #include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <unistd.h>
 
 #include <complex>
+#include <fstream>
+#include <iostream>
 #include <cstddef>
 #include <string>
 
 #include "cognitive_engine.hpp"
+#include "timer.h"
+
+// transmitter / receiver states, as upstream (include/extensible_cognitive_radio.hpp:31-44)
+enum tx_states { TX_STOPPED = 0, TX_CONTINUOUS, TX_BURST };
+enum rx_states { RX_STOPPED = 0, RX_CONTINUOUS };
 
 // A stand-in for uhd::device::recv(..., RECV_MODE_ONE_PACKET) (cpp:1304-1306).
 class IqSource {
@@ -90,6 +106,8 @@ public:
   double get_rx_rate();
   void start_tx();
   void stop_tx();
+  int get_tx_state();
+  int get_rx_state();
   void start_rx();
   void stop_rx();
 

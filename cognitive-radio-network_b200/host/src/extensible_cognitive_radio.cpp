@@ -128,6 +128,9 @@ double ExtensibleCognitiveRadio::get_rx_rate() { double v; LOCKED(rx_params_mute
 void ExtensibleCognitiveRadio::start_tx() { LOCKED(tx_params_mutex, tx_on_ = true); }
 void ExtensibleCognitiveRadio::stop_tx() { LOCKED(tx_params_mutex, tx_on_ = false); }
 
+int ExtensibleCognitiveRadio::get_tx_state() { int v; LOCKED(tx_params_mutex, v = tx_on_ ? TX_CONTINUOUS : TX_STOPPED); return v; }
+int ExtensibleCognitiveRadio::get_rx_state() { int v; LOCKED(rx_params_mutex, v = rx_running ? RX_CONTINUOUS : RX_STOPPED); return v; }
+
 void ExtensibleCognitiveRadio::start_rx() {
   pthread_mutex_lock(&rx_params_mutex);
   rx_running = true;

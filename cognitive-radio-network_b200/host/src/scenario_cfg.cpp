@@ -1,6 +1,7 @@
 #include "scenario_cfg.hpp"
 
 #include <ctype.h>
+#include <getopt.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -153,4 +154,5 @@ void cfg_str2argcargv(const std::string &args, const std::string &prog, int *arg
   *argv = (char **)malloc(sizeof(char *) * (tok.size() + 1));
   for (size_t k = 0; k < tok.size(); k++) (*argv)[k] = strdup(tok[k].c_str());
   (*argv)[tok.size()] = NULL;
+  optind = 0;  // as upstream (src/crts.cpp:80): engines call getopt() on this argv from scratch
 }

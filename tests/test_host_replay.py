@@ -65,6 +65,72 @@ def test_replay_fails_loudly_without_gpu_or_inputs(replay, tmp_path):
         assert "crn_create failed" in r.stdout and "no usable CUDA device" in r.stdout
 
 
+REF_ENGINES = "/root/reference/cognitive_engines"
+
+
+def _make(out, engine_dirs, skip="", extra_inc="", extra_srcs=""):
+    cmd = ["make", "-s", "-C", HOST, "OUT=%s" % out, "ENGINE_DIRS=%s" % engine_dirs]
+    if skip:
+        cmd.append("SKIP=%s" % skip)
+    if extra_inc:
+        cmd.append("EXTRA_INC=%s" % extra_inc)
+    if extra_srcs:
+        cmd.append("EXTRA_SRCS=%s" % extra_srcs)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return os.path.join(str(out), "crn_replay")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ENGINES), reason="reference tree not present (GPU box)")
+def test_reference_engines_build_unmodified_and_register(crn, tmp_path):
+    """the other engines of the reference (CE_Template, CE_TX_CHANNEL_X,
+    CE_Random_Behaviour_PU, CE_PU_MARKOV_Chain_Tx) compile from where they lie, unmodified, against this
+    radio's headers, and the registration generator wires them up next to the GPU-backed CE_Predictive_Node
+    (ours is found first, so the reference's CPU engine of the same name is skipped)."""
+    exe = _make(tmp_path, "%s %s" % (os.path.join(HOST, "cognitive_engines"), REF_ENGINES))
+    reg = open(os.path.join(str(tmp_path), "lib", "ce_registry_generated.cpp")).read()
+    for name in ("CE_Predictive_Node", "CE_Template", "CE_TX_CHANNEL_X", "CE_Random_Behaviour_PU", "CE_PU_MARKOV_Chain_Tx"):
+        assert "CRN_REGISTER_CE(%s)" % name in reg
+    assert reg.count("CE_Predictive_Node.hpp") == 1 and REF_ENGINES + "/CE_Predictive_Node" not in reg
+    # run one of them: CE_Template only looks at CE_metrics.CE_event (CE_Template.cpp:33-60)
+    cfg = tmp_path / "t.cfg"
+    cfg.write_text('node1 : { cognitive_engine = "CE_Template"; ce_timeout_ms = 0; ce_args = "-d 1"; rx_freq = 833e6; rx_rate = 13e6; };')
+    iq = tmp_path / "z.c64"
+    np.zeros(512 * 40, np.complex64).tofile(iq)
+    r = run(exe, ["--scenario", str(cfg), "--node", "1", "--iq", str(iq), "--packet-len", "512", "--free-run"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "engine=CE_Template" in r.stdout and "40 packets received" in r.stdout
+    # the PU engine the shipped scenario uses starts too (it only retunes every 2 s of wall clock)
+    cfg.write_text('node1 : { cognitive_engine = "CE_Random_Behaviour_PU"; ce_timeout_ms = 0; tx_freq = 833e6; };')
+    r = run(exe, ["--scenario", str(cfg), "--node", "1", "--iq", str(iq), "--packet-len", "512", "--free-run"])
+    assert r.returncode == 0 and "final tx_freq=833000000 Hz" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ENGINES), reason="reference tree not present (GPU box)")
+def test_reference_cpu_engine_on_this_radio_reproduces_the_fixtures(crn, tmp_path):
+    """The radio runtime itself is checked with the reference's UNMODIFIED CPU CE_Predictive_Node plugged into
+    it (liquid's FFT replaced by the oracle's restatement - test infrastructure): the lock-step handoff must
+    deliver every packet exactly once, in order, so the engine's printed decisions equal the fixtures."""
+    oracle_dir = os.path.join(ROOT, "oracle")
+    fft_obj = str(tmp_path / "liquid_fft_restated.o")
+    subprocess.run(["gcc", "-O2", "-c", "%s/liquid_fft_restated.c" % oracle_dir, "-o", fft_obj], check=True)
+    exe = _make(tmp_path, REF_ENGINES, extra_inc="-I %s/compat" % oracle_dir, extra_srcs=fft_obj)
+    g = np.load(os.path.join(GOLDEN, "ref_markov_L363.npz"))
+    iq = tmp_path / "cap.c64"
+    g["iq"].astype(np.complex64).tofile(iq)
+    r = run(exe, ["--scenario", SCENARIO, "--node", "2", "--iq", str(iq), "--packet-len", "363", "--ce-args", ""])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+    import re
+    got = []
+    for m in re.finditer(r"Channel_State\[(\d)\]: OCCUPIED|ALL BUSY", r.stdout):
+        got.append(int(m.group(1)) if m.group(1) else 0)
+    assert got == g["decision"].tolist()
+    feats = re.findall(r"NOISE FLOOR\s+(\S+)\s+CH1\s+(\S+)\s+CH2\s+(\S+)\s+CH3\s+(\S+)", r.stdout)
+    printed = np.array(feats, dtype=np.float64)
+    assert np.allclose(printed, g["feat"], rtol=6e-3)   # printed at %.2e upstream (.cpp:207)
+    assert "%d forwarded to the CE" % (10 * len(got)) in r.stdout
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["ref_markov_L512", "ref_markov_L363", "ref_tone70"])
 def test_replayed_capture_matches_reference_engine_fixtures(crn, replay, tmp_path, case):
