@@ -45,10 +45,31 @@ def _oracle():
     return oracle
 
 
+WORKLOADS = {
+    # name: (description, builder(crn) -> (cfg, ngroups, streams))
+    "config2": WORKLOAD,
+    "wideband": "configs[2]: wideband sweep, 8192-pt FFT, 64 equal sub-channels, 100 MHz equivalent rate, energy-detection features, 64-frame average, 1e9 complex-float samples",
+    "multiradio": "configs[3]: multi-radio, 4096 independent sensing streams (simulated CORNET nodes), 2048-pt FFT, 64-frame Welch average + ANN, one decision per stream (537e6 samples)",
+    "refexact": "configs[0] on the GPU: reference-exact mode, 512-pt FFT, no window, |X| averaged over 10 frames, (sum)^2 features + ANN, 1e9 complex-float samples",
+}
+ACTIVE = {"name": "config2"}
+
+
 def workload_config(crn):
+    """Returns (cfg, decision groups per GPU).  The default - and the only bench line the contract asks for -
+    is BASELINE configs[1]; the others are the remaining BASELINE configs, selectable with --workload."""
+    w = ACTIVE["name"]
+    if w == "wideband":
+        cfg = crn.config_wideband(8192, 64, 64)
+        return cfg, TOTAL_SAMPLES // cfg.group_samples
+    if w == "multiradio":
+        cfg = crn.config_welch(2048, 64)
+        return cfg, 4096
+    if w == "refexact":
+        cfg = crn.config_reference()
+        return cfg, TOTAL_SAMPLES // cfg.group_samples
     cfg = crn.config_welch(NFFT, NAVG)
-    ngroups = TOTAL_SAMPLES // cfg.group_samples  # 15258 full decisions, remainder dropped
-    return cfg, ngroups
+    return cfg, TOTAL_SAMPLES // cfg.group_samples  # 15258 full decisions, remainder dropped
 
 
 def synth_cfg(crn, cfg):
@@ -57,7 +78,7 @@ def synth_cfg(crn, cfg):
 
 
 def base_config(extra=None):
-    c = {"workload": WORKLOAD, "nfft": NFFT, "navg": NAVG, "window": "hann(liquid, symmetric)",
+    c = {"workload": WORKLOADS[ACTIVE["name"]], "nfft": NFFT, "navg": NAVG, "window": "hann(liquid, symmetric)",
          "detector": "|X|^2", "bands": "NF,CH1,CH2,CH3 (reference bin plan x2)", "ann": "4-5-3 logistic, fp64",
          "samples_per_gpu": None, "l2": "input 8 GB >> 126 MB L2, no flush needed",
          "synthetic": "OFDM PU (64 sc, cp16, taper4, 1.4->13 MS/s) hopping 833/835/838 MHz by the documented Markov matrix + AWGN, SNR 10 dB, seed 12"}
@@ -274,7 +295,10 @@ def run_ours(args):
     # ---- synthetic capture, generated in HBM (rank r owns samples [r*nsamp, (r+1)*nsamp)) -------------
     d_iq = torch.empty(nsamp, 2, dtype=torch.float32, device=dev)
     d_state = torch.empty(ngroups, dtype=torch.int32, device=dev)
-    crn.synth_generate(synth_cfg(crn, cfg), d_iq, rank * nsamp, nsamp, d_state, local_rank, stream)
+    if ACTIVE["name"] == "multiradio":   # rank r owns streams [r*ngroups, (r+1)*ngroups), one group each
+        crn.synth_generate_streams(synth_cfg(crn, cfg), d_iq, rank * ngroups, ngroups, gs, d_state, local_rank, stream)
+    else:
+        crn.synth_generate(synth_cfg(crn, cfg), d_iq, rank * nsamp, nsamp, d_state, local_rank, stream)
     d_feat = torch.empty(ngroups, cfg.nbands, dtype=torch.float32, device=dev)
     d_ann = torch.empty(ngroups, 3, dtype=torch.float64, device=dev)
     d_dec = torch.empty(ngroups, dtype=torch.int32, device=dev)
@@ -364,7 +388,8 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": base_config({"samples_per_gpu": nsamp, "groups_per_gpu": ngroups, "kernel": info}),
+            "config": base_config({"samples_per_gpu": nsamp, "groups_per_gpu": ngroups, "kernel": info,
+                                   "nfft": cfg.nfft, "navg": cfg.navg, "nbands": cfg.nbands}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
             "cpu_baseline": cpu, "parity_check": parity, "decision_histogram": dec_hist.cpu().tolist(),
             "ms_per_step_minmax": [min(step_ms), max(step_ms)]}
@@ -383,7 +408,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
+                    help="default = BASELINE configs[1] (the contract's bench line); others = remaining BASELINE configs")
     args = ap.parse_args()
+    ACTIVE["name"] = args.workload
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

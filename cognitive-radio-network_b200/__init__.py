@@ -104,6 +104,7 @@ API = {
     "crn_sense_batch_device": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "crn_synth_config_default": (C.c_int, [C.POINTER(SynthConfig), C.c_int32]),
     "crn_synth_generate_device": (C.c_int, [C.POINTER(SynthConfig), C.c_int32, _P, C.c_int64, C.c_int64, _P, _P]),
+    "crn_synth_generate_streams_device": (C.c_int, [C.POINTER(SynthConfig), C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "crn_strerror": (C.c_char_p, [C.c_int]),
     "crn_last_error": (C.c_char_p, []),
     "crn_version": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -303,6 +304,13 @@ def synth_generate(sc, d_iq, first_sample, nsamples, d_state=None, device=0, str
     """Fill a device tensor with the synthetic Markov-PU OFDM + AWGN capture (see crn_synth.cu)."""
     _check(lib.crn_synth_generate_device(C.byref(sc), device, _ptr(d_iq), first_sample, nsamples,
                                          _ptr(d_state), C.c_void_p(stream)), "crn_synth_generate_device")
+
+
+def synth_generate_streams(sc, d_iq, first_stream, nstreams, samples_per_stream, d_state=None, device=0, stream=0):
+    """Independent streams (multi-radio): stream first_stream + i -> d_iq[i * samples_per_stream : ...]."""
+    _check(lib.crn_synth_generate_streams_device(C.byref(sc), device, _ptr(d_iq), first_stream, nstreams,
+                                                 samples_per_stream, _ptr(d_state), C.c_void_p(stream)),
+           "crn_synth_generate_streams_device")
 
 
 def shard_groups(ngroups, world_size, rank):

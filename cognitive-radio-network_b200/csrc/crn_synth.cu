@@ -32,7 +32,7 @@ __host__ __device__ inline unsigned long long mix64(unsigned long long x) {
   return x ^ (x >> 31);
 }
 
-inline unsigned long long stream_seed(unsigned long long seed, long long stream) {
+__host__ __device__ inline unsigned long long stream_seed(unsigned long long seed, long long stream) {
   return mix64(seed ^ mix64((unsigned long long)stream * 0xD1B54A32D192ED03ull + 1));
 }
 
@@ -47,10 +47,11 @@ int pu_next(int mode, int cur, int r) {
 
 struct SynthParams {
   float2 *iq;
-  const signed char *states;  // [ndwell]
-  int *group_state;           // [ngroups] or nullptr
-  unsigned long long sseed;
-  long long first, n;
+  const signed char *states;  // [nstreams][ndwell]
+  int *group_state;           // [nstreams][groups per stream] or nullptr
+  unsigned long long seed;    // base seed; stream i uses stream_seed(seed, first_stream + i)
+  long long first_stream, sps, ndwell;  // samples per stream, dwells per stream
+  long long first, n;         // first sample index inside a stream (single-stream mode), total samples
   long long dwell_samples;
   int group_samples;
   float gain, sigc;
@@ -75,9 +76,12 @@ __device__ __forceinline__ void subcarrier(unsigned long long sseed, long long m
 __global__ void __launch_bounds__(256) synth_kernel(const SynthParams p) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
-    const long long s = p.first + i;
-    const int ch = p.states[s / p.dwell_samples];
-    if (p.group_state && (s % p.group_samples) == 0) p.group_state[s / p.group_samples - p.first / p.group_samples] = ch;
+    const long long si = i / p.sps;                 // stream slot in this call
+    const long long s = p.first + (i - si * p.sps);  // sample index inside the stream
+    const unsigned long long sseed = stream_seed(p.seed, p.first_stream + si);
+    const int ch = p.states[si * p.ndwell + s / p.dwell_samples];
+    if (p.group_state && (s % p.group_samples) == 0)
+      p.group_state[si * (p.sps / p.group_samples) + s / p.group_samples - p.first / p.group_samples] = ch;
     const long long un = s * SY_RATE_NUM;
     const long long m = un / ((long long)SY_RATE_DEN * SY_SYM);
     const float tau = (float)(un % ((long long)SY_RATE_DEN * SY_SYM)) / (float)SY_RATE_DEN;
@@ -94,13 +98,13 @@ __global__ void __launch_bounds__(256) synth_kernel(const SynthParams p) {
 #pragma unroll 5
     for (int k = 1; k <= SY_HALF; k++) {
       float xr, xi, yr, yi;
-      subcarrier(p.sseed, m, k, xr, xi);
-      subcarrier(p.sseed, m, -k, yr, yi);
+      subcarrier(sseed, m, k, xr, xi);
+      subcarrier(sseed, m, -k, yr, yi);
       ar += xr * pr - xi * pi + yr * pr + yi * pi;
       ai += xr * pi + xi * pr - yr * pi + yi * pr;
       if (in_taper) {
-        subcarrier(p.sseed, m - 1, k, xr, xi);
-        subcarrier(p.sseed, m - 1, -k, yr, yi);
+        subcarrier(sseed, m - 1, k, xr, xi);
+        subcarrier(sseed, m - 1, -k, yr, yi);
         br += xr * pr - xi * pi + yr * pr + yi * pi;
         bi += xr * pi + xi * pr - yr * pi + yi * pr;
       }
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(256) synth_kernel(const SynthParams p) {
     float cr, ci;
     sincosf(6.283185307179586f * ph, &ci, &cr);
     float outr = vr * cr - vi * ci, outi = vr * ci + vi * cr;
-    const unsigned long long h = mix64(p.sseed ^ mix64(2ull * (unsigned long long)s + 1ull));
+    const unsigned long long h = mix64(sseed ^ mix64(2ull * (unsigned long long)s + 1ull));
     const float u1 = (float)((h >> 40) + 1ull) * (1.0f / 16777216.0f);
     const float u2 = (float)((h >> 16) & 0xFFFFFFull) * (1.0f / 16777216.0f);
     const float rad = p.sigc * sqrtf(-2.0f * logf(u1));
@@ -129,14 +133,10 @@ __global__ void __launch_bounds__(256) synth_kernel(const SynthParams p) {
 
 }  // namespace
 
-extern "C" int crn_synth_generate_device(const crn_synth_config *sc, int32_t device, void *d_iq,
-                                         int64_t first_sample, int64_t nsamples, int32_t *d_state,
-                                         void *cuda_stream) {
-  if (!sc || !d_iq || first_sample < 0 || nsamples < 0 || sc->group_samples < 1 || sc->dwell_groups < 1)
-    return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_device: bad argument");
-  if (d_state && (first_sample % sc->group_samples) != 0)
-    return crn::fail(CRN_ERR_INVALID, "first_sample must be group aligned when d_state is requested");
-  if (nsamples == 0) return CRN_OK;
+namespace {
+int synth_launch(const crn_synth_config *sc, int32_t device, void *d_iq, int64_t first_stream, int64_t nstreams,
+                 int64_t first_sample, int64_t sps, int32_t *d_state, void *cuda_stream) {
+  if (sps == 0 || nstreams == 0) return CRN_OK;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return crn::fail(CRN_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -145,9 +145,11 @@ extern "C" int crn_synth_generate_device(const crn_synth_config *sc, int32_t dev
   memset(&p, 0, sizeof(p));
   p.iq = (float2 *)d_iq;
   p.group_state = d_state;
-  p.sseed = stream_seed(sc->seed, 0);
+  p.seed = sc->seed;
+  p.first_stream = first_stream;
+  p.sps = sps;
   p.first = first_sample;
-  p.n = nsamples;
+  p.n = sps * nstreams;
   p.dwell_samples = (long long)sc->dwell_groups * sc->group_samples;
   p.group_samples = sc->group_samples;
   p.gain = (float)pow(10.0, sc->pu_gain_db / 20.0);
@@ -157,29 +159,33 @@ extern "C" int crn_synth_generate_device(const crn_synth_config *sc, int32_t dev
   p.sigc = (float)sqrt(sigma2 / 2.0);
   for (int c = 0; c < 3; c++) p.cyc_per_sample[c] = sc->offsets_hz[c] / sc->fs;
 
-  // walk the hop chain on the host from dwell 0 (it is sequential by definition) and upload it
-  const long long ndwell = (first_sample + nsamples + p.dwell_samples - 1) / p.dwell_samples;
-  std::vector<signed char> states((size_t)ndwell);
-  int cur = 0;  // dwell 0 on CH1: tx_freq = 833e6, scenarios/predictive_model.cfg:37
-  for (long long d = 0; d < ndwell; d++) {
-    if (d > 0) {
-      const unsigned long long h = mix64(p.sseed ^ (0xA5A5A5A5ull + (unsigned long long)d * 0x2545F4914F6CDD1Dull));
-      const int r = (sc->hop_mode == 2) ? (int)((h >> 33) % 3) : (int)((h >> 33) % 10);
-      cur = pu_next(sc->hop_mode, cur, r);
+  // walk every stream's hop chain on the host from dwell 0 (sequential by definition) and upload it
+  const long long ndwell = (first_sample + sps + p.dwell_samples - 1) / p.dwell_samples;
+  p.ndwell = ndwell;
+  std::vector<signed char> states((size_t)(ndwell * nstreams));
+  for (long long si = 0; si < nstreams; si++) {
+    const unsigned long long sseed = stream_seed(sc->seed, first_stream + si);
+    int cur = 0;  // dwell 0 on CH1: tx_freq = 833e6, scenarios/predictive_model.cfg:37
+    for (long long d = 0; d < ndwell; d++) {
+      if (d > 0) {
+        const unsigned long long h = mix64(sseed ^ (0xA5A5A5A5ull + (unsigned long long)d * 0x2545F4914F6CDD1Dull));
+        const int r = (sc->hop_mode == 2) ? (int)((h >> 33) % 3) : (int)((h >> 33) % 10);
+        cur = pu_next(sc->hop_mode, cur, r);
+      }
+      states[(size_t)(si * ndwell + d)] = (signed char)cur;
     }
-    states[(size_t)d] = (signed char)cur;
   }
   signed char *d_states = nullptr;
-  e = cudaMallocAsync(&d_states, (size_t)ndwell, st);
+  e = cudaMallocAsync(&d_states, states.size(), st);
   if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaMallocAsync: %s", cudaGetErrorString(e));
-  e = cudaMemcpyAsync(d_states, states.data(), (size_t)ndwell, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
   // pageable source: the copy is staged before the call returns, `states` may go out of scope
+  e = cudaMemcpyAsync(d_states, states.data(), states.size(), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
   p.states = d_states;
 
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
-  long long blocks = (nsamples + 255) / 256;
+  long long blocks = (p.n + 255) / 256;
   const long long cap = (long long)dev_sms * 8;
   if (blocks > cap) blocks = cap;
   synth_kernel<<<(int)blocks, 256, 0, st>>>(p);
@@ -188,4 +194,27 @@ extern "C" int crn_synth_generate_device(const crn_synth_config *sc, int32_t dev
   e = cudaFreeAsync(d_states, st);
   if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaFreeAsync: %s", cudaGetErrorString(e));
   return CRN_OK;
+}
+}  // namespace
+
+extern "C" int crn_synth_generate_device(const crn_synth_config *sc, int32_t device, void *d_iq,
+                                         int64_t first_sample, int64_t nsamples, int32_t *d_state,
+                                         void *cuda_stream) {
+  if (!sc || !d_iq || first_sample < 0 || nsamples < 0 || sc->group_samples < 1 || sc->dwell_groups < 1)
+    return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_device: bad argument");
+  if (d_state && ((first_sample % sc->group_samples) != 0 || (nsamples % sc->group_samples) != 0))
+    return crn::fail(CRN_ERR_INVALID, "first_sample and nsamples must be group aligned when d_state is requested");
+  return synth_launch(sc, device, d_iq, 0, 1, first_sample, nsamples, d_state, cuda_stream);
+}
+
+extern "C" int crn_synth_generate_streams_device(const crn_synth_config *sc, int32_t device, void *d_iq,
+                                                 int64_t first_stream, int64_t nstreams,
+                                                 int64_t samples_per_stream, int32_t *d_state,
+                                                 void *cuda_stream) {
+  if (!sc || !d_iq || first_stream < 0 || nstreams < 0 || samples_per_stream < 0 || sc->group_samples < 1 ||
+      sc->dwell_groups < 1)
+    return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_streams_device: bad argument");
+  if (d_state && (samples_per_stream % sc->group_samples) != 0)
+    return crn::fail(CRN_ERR_INVALID, "samples_per_stream must be group aligned when d_state is requested");
+  return synth_launch(sc, device, d_iq, first_stream, nstreams, 0, samples_per_stream, d_state, cuda_stream);
 }

@@ -195,6 +195,13 @@ int crn_synth_generate_device(const crn_synth_config *sc, int32_t device, void *
                               int64_t first_sample, int64_t nsamples, int32_t *d_state,
                               void *cuda_stream);
 
+/* Multi-radio variant (BASELINE configs[3]: independent sensing streams, simulated CORNET nodes): stream
+   first_stream + i has its own seed, hop chain and noise, starts at its sample 0 and is written to
+   d_iq + i * samples_per_stream.  d_state (optional): int32[nstreams][samples_per_stream / group_samples]. */
+int crn_synth_generate_streams_device(const crn_synth_config *sc, int32_t device, void *d_iq,
+                                      int64_t first_stream, int64_t nstreams, int64_t samples_per_stream,
+                                      int32_t *d_state, void *cuda_stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 
 const char *crn_strerror(int status);

@@ -288,6 +288,42 @@ def test_synth_kernel_matches_cpu_statement(crn, oracle, torch):
     assert np.array_equal(d_part.cpu().numpy().view(np.complex64).ravel(), got[2 * gs: 2 * gs + 1000])
 
 
+def test_multi_radio_streams(crn, oracle, torch):
+    """BASELINE configs[3] shape: independent sensing streams (simulated CORNET nodes), 2048-pt FFT, one
+    decision group per stream, every stream with its own seed / hop chain / noise."""
+    cfg = crn.config_welch(2048, 8)
+    gs = cfg.group_samples
+    nstreams, gps = 96, 3                      # 3 decisions per stream
+    sps = gps * gs
+    sc = crn.synth_config(gs, dwell_groups=1, snr_db=10.0, seed=12)
+    d_iq = torch.empty(nstreams * sps, 2, dtype=torch.float32, device="cuda")
+    d_state = torch.full((nstreams, gps), -1, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    crn.synth_generate_streams(sc, d_iq, 1000, nstreams, sps, d_state, 0, stream)   # streams 1000..1095
+    ng = nstreams * gps
+    d_feat = torch.empty(ng, 4, dtype=torch.float32, device="cuda")
+    d_ann = torch.empty(ng, 3, dtype=torch.float64, device="cuda")
+    d_dec = torch.empty(ng, dtype=torch.int32, device="cuda")
+    with crn.Sensor(cfg, device=0) as s:
+        s.sense_device(d_iq, ng, d_feat, d_ann, d_dec, None, stream)
+    torch.cuda.synchronize()
+    iq = d_iq.cpu().numpy().view(np.complex64).reshape(nstreams, sps)
+    states = d_state.cpu().numpy()
+    feat = d_feat.cpu().numpy().reshape(nstreams, gps, 4)
+    dec = d_dec.cpu().numpy().reshape(nstreams, gps)
+    seen = set()
+    for i in (0, 1, 37, 95):
+        want_iq, want_states = oracle.synth(sc, sps, stream=1000 + i)
+        assert np.array_equal(states[i], want_states[:gps])
+        assert np.abs(iq[i] - want_iq).max() <= 2e-4
+        of, oa, od, _ = oracle.sense_port(cfg, iq[i])          # oracle on the GPU-generated samples
+        assert feat_close(feat[i], of, FEAT_RTOL) and np.array_equal(dec[i], od)
+        seen.update(states[i].tolist())
+    assert not np.array_equal(iq[0], iq[1])                    # streams really are independent
+    # the MLP tracks each stream's own primary user
+    assert (dec == states + 1).mean() > 0.9 and len(set(states.ravel().tolist())) == 3
+
+
 def test_full_size_parseval_and_sampled_parity(crn, oracle, torch):
     """BASELINE config 2 at full size (1e9 complex samples resident in HBM): (i) Parseval - with a band
     plan that tiles all N bins, sum_bands mean_k sum_bins |X|^2 == N * mean_k sum_n |w x|^2, checked per
