@@ -130,6 +130,15 @@ void build_twiddles(const crn::RadixPlan &rp, std::vector<float4> &tw) {
         tw.push_back(make_float4((float)cos(a), (float)sin(a), (float)cos(b), (float)sin(b)));
       }
   };
+  if (rp.hybrid) {
+    // hybrid plan: the 1024-point 32x32 table, then W_N^n for n < 1024 (1024 float2 packed as 512 float4)
+    add(32, 32);
+    for (int n = 0; n < 1024; n += 2) {
+      const double a0 = -2.0 * M_PI * (double)n / (double)rp.n, a1 = -2.0 * M_PI * (double)(n + 1) / (double)rp.n;
+      tw.push_back(make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1)));
+    }
+    return;
+  }
   add(rp.r0, rp.r1);
   if (rp.r2 > 1) add(rp.r0 * rp.r1, rp.r2);
 }

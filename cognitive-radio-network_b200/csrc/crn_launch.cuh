@@ -82,16 +82,16 @@ int launch_sense_8192(const SenseParams &, int, int, int, cudaStream_t, LaunchGe
 
 // Radix plan per size (must match the Plan<> in crn_sense_n<N>.cu): the host builds the paired twiddle
 // and window tables from it.
-struct RadixPlan { int n, e, r0, r1, r2; };
+struct RadixPlan { int n, e, r0, r1, r2; bool hybrid; };
 inline RadixPlan radix_plan(int n) {
   switch (n) {
-    case 256: return {256, 16, 16, 16, 1};
-    case 512: return {512, 32, 32, 16, 1};
-    case 1024: return {1024, 32, 32, 32, 1};
-    case 2048: return {2048, 32, 32, 8, 8};
-    case 4096: return {4096, 16, 16, 16, 16};
-    case 8192: return {8192, 32, 32, 16, 16};
-    default: return {0, 0, 0, 0, 0};
+    case 256: return {256, 16, 16, 16, 1, false};
+    case 512: return {512, 32, 32, 16, 1, false};
+    case 1024: return {1024, 32, 32, 32, 1, false};
+    case 2048: return {2048, 32, 2, 32, 32, true};
+    case 4096: return {4096, 32, 4, 32, 32, true};
+    case 8192: return {8192, 32, 8, 32, 32, true};
+    default: return {0, 0, 0, 0, 0, false};
   }
 }
 

@@ -73,6 +73,11 @@ struct Plan {
   static constexpr int UNIT_THREADS = T > 32 ? T : 32;
   static constexpr int UNITS = NT / UNIT_THREADS;  // reduction units per CTA
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
+  static constexpr bool HYBRID = false;
+  static constexpr int C = 1;
+  static constexpr bool WIN_SMEM = true;           // window table staged in shared memory
+  // spectrum bin held in accumulator register m of team thread t after the last pass
+  __host__ __device__ static constexpr int bin_of(int t, int m) { return t + T * m; }
   // Bulk-copy (TMA) staging of the next frame pays off where a frame spans several warps and every
   // exchange is a multi-warp barrier (measured: +8 % at N = 4096, +13 % at N = 8192); for the one-warp-
   // per-frame sizes plain coalesced loads plus the L2 prefetch are faster and leaner in registers.
@@ -93,6 +98,50 @@ struct Plan {
   static_assert(NT % UNIT_THREADS == 0 && (T <= 32 || UNITS <= 15), "units must tile the CTA (named barriers 1..15)");
   static constexpr size_t smem_bytes(bool win) {
     return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win ? N / 2 : 0)) +
+           sizeof(float) * (2 * UNITS * CRN_MAX_SEGS + CRN_MAX_BANDS * UNITS) + sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
+  }
+};
+
+// Plan for N = C * 1024, C in {2, 4, 8}: "one cross-warp step, then every warp on its own".
+//   pass A   radix-C decimation in frequency across the frame's C 1024-sample segments (registers
+//            {i + r*G}, G = 32/C; window folded in), then the DIF twiddles W_N^(n r) - built from ONE table
+//            value W_N^n per n by squaring/multiplying, so the table is 8 KB whatever N is;
+//   exchange the only team-wide one: sub-sequence y_r goes to warp r;
+//   pass B,C warp r runs the 1024-point 32x32 FFT of y_r with warp-local synchronisation only, exactly as
+//            the N = 1024 kernel does; it ends up holding bins C*k + r.
+// Against the generic three-pass plans this halves the multi-warp barriers per frame, needs ~128 instead of
+// 170-230 registers and a third less shared memory (two CTAs per SM at N = 8192).
+template <int N_, int TEAMS_, int MINB_>
+struct HybridPlan {
+  static constexpr int N = N_, E = 32, TEAMS = TEAMS_, MINB = MINB_;
+  static constexpr int C = N / 1024;
+  static constexpr int R0 = C, R1 = 32, R2 = 32;   // reported in the kernel name
+  static constexpr int T = N / E;                  // 32*C threads = C warps per frame
+  static constexpr int NT = T * TEAMS;
+  static constexpr int PASSES = 3;
+  static constexpr int PADSHIFT = 5;
+  static constexpr int RS = 32 * (32 + 2);         // float2 slots of one warp's region (padded 32x32 exchange)
+  static constexpr int XSZ = C * RS;
+  static constexpr int TW1 = 512;                  // paired 32x32 twiddles of the 1024-point FFT (float4)
+  static constexpr int TW2 = 512;                  // W_N^n, n < 1024, as 1024 float2 = 512 float4
+  static constexpr int UNIT_THREADS = T;
+  static constexpr int UNITS = TEAMS;
+  static constexpr int TEAMS_PER_UNIT = 1;
+  static constexpr bool HYBRID = true;
+  static constexpr bool TMA = false;
+  // At N = 8192 the 32 KB window table is what keeps a second CTA off the SM; there it is read through the
+  // read-only L1 path instead (the table is reused by every frame, L1 keeps it).
+  static constexpr bool WIN_SMEM = (N < 8192);
+#ifdef CRN_NO_PREFETCH
+  static constexpr bool PREFETCH = false;
+#else
+  static constexpr bool PREFETCH = true;
+#endif
+  static_assert(C == 2 || C == 4 || C == 8, "hybrid plans cover N = 2048, 4096, 8192");
+  static_assert(UNITS <= 15, "named barriers 1..15");
+  __host__ __device__ static constexpr int bin_of(int t, int m) { return C * ((t & 31) + 32 * m) + (t >> 5); }
+  static constexpr size_t smem_bytes(bool win) {
+    return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win && WIN_SMEM ? N / 2 : 0)) +
            sizeof(float) * (2 * UNITS * CRN_MAX_SEGS + CRN_MAX_BANDS * UNITS) + sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
   }
 };
@@ -228,6 +277,23 @@ __device__ __forceinline__ void reg_pass_tw(float2 (&a)[E], const float4 *__rest
 #else
 #define CRN_XPAD 2  // 16-byte exchange stores need 16-byte aligned rows
 #endif
+// DIF twiddles of the hybrid plan: register i + r*G holds z_r[n] with n = t + T*i; multiply by W_N^(n r).
+// Only W_N^n comes from the table; the powers are built by squaring / one multiplication each.
+template <int E, int C, int T>
+__device__ __forceinline__ void hybrid_twiddle(float2 (&a)[E], const float2 *__restrict__ twA, int t) {
+  constexpr int G = E / C;
+  static_for<0, G>([&](auto I) {
+    const float2 w1 = twA[t + T * I.value];
+    float2 w[C];
+    w[1] = w1;
+    static_for<2, C>([&](auto R) {
+      if constexpr (R.value % 2 == 0) w[R.value] = cmul(w[R.value / 2], w[R.value / 2]);
+      else w[R.value] = cmul(w[R.value - 1], w1);
+    });
+    static_for<1, C>([&](auto R) { a[I.value + R.value * G] = cmul(a[I.value + R.value * G], w[R.value]); });
+  });
+}
+
 template <int PADSHIFT>
 __device__ __forceinline__ int xphys(int idx) {
   return idx + CRN_XPAD * (idx >> PADSHIFT);
@@ -340,8 +406,10 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
   float4 *tw1 = reinterpret_cast<float4 *>(smem_raw);
   float4 *tw2 = tw1 + P::TW1;
   float2 *xbuf = reinterpret_cast<float2 *>(tw2 + P::TW2);
-  float2 *winp = xbuf + (size_t)TEAMS * P::XSZ;
-  float *segpart = reinterpret_cast<float *>(winp + (WIN ? N / 2 : 0));  // [2][UNITS][CRN_MAX_SEGS]
+  float2 *winp_s = xbuf + (size_t)TEAMS * P::XSZ;
+  constexpr bool WSM = WIN && P::WIN_SMEM;
+  const float2 *winp = WSM ? winp_s : prm.winp;  // window pairs: shared copy, or read-only global path
+  float *segpart = reinterpret_cast<float *>(winp_s + (WSM ? N / 2 : 0));  // [2][UNITS][CRN_MAX_SEGS]
   float *featbuf = segpart + 2 * UNITS * CRN_MAX_SEGS;                    // [UNITS][CRN_MAX_BANDS]
   int *cnt = reinterpret_cast<int *>(featbuf + UNITS * CRN_MAX_BANDS);    // [2][UNITS] arrivals
   volatile int *done = cnt + 2 * UNITS;                                   // [2][UNITS] completed combines
@@ -363,8 +431,8 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
 
   // one-time table staging (persistent CTA: amortised over all its groups)
   for (int i = tid; i < P::TW1 + P::TW2; i += NT) tw1[i] = prm.tw[i];
-  if constexpr (WIN)
-    for (int i = tid; i < N / 2; i += NT) winp[i] = prm.winp[i];
+  if constexpr (WSM)
+    for (int i = tid; i < N / 2; i += NT) winp_s[i] = prm.winp[i];
   for (int i = tid; i < 4 * UNITS; i += NT) cnt[i] = 0;
   const bool tma = P::TMA && (EPI == EPI_CTA) && prm.use_tma;
   if (tma && t == 0) {
@@ -418,6 +486,27 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
 #pragma unroll
         for (int m = 0; m < E; m++) a[m] = (t + T * m < L) ? ld_stream(x + T * m) : make_float2(0.f, 0.f);
       }
+      if constexpr (P::HYBRID) {
+        constexpr int C = P::C, G = E / C;
+        // pass A: radix-C across the frame's C segments (window folded in), then the DIF twiddles
+        reg_pass_first<E, C, T, WIN>(a, winp, t);
+        hybrid_twiddle<E, C, T>(a, reinterpret_cast<const float2 *>(tw2), t);
+        // the one team-wide exchange: y_r[n] (n = t + T*i) goes to warp r's region, linear in n
+        team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
+        static_for<0, G>([&](auto I) {
+          static_for<0, C>([&](auto R) { xb[R.value * P::RS + t + T * I.value] = a[I.value + R.value * G]; });
+        });
+        team_sync<T>(team);
+        const int lane = t & 31;
+        float2 *wb = xb + (t >> 5) * P::RS;
+#pragma unroll
+        for (int m = 0; m < E; m++) a[m] = wb[lane + 32 * m];
+        // warp r: 1024-point FFT of y_r, warp-local from here on (same code as the N = 1024 kernel)
+        __syncwarp();  // the region is rewritten in padded layout below
+        reg_pass_first<E, 32, 32, false>(a, winp, lane);
+        exchange<E, 32, 32, 1, 5>(a, wb, lane, 0);
+        reg_pass_tw<E, 32, 32, 32>(a, tw1, lane);
+      } else {
       // pass 0 (Ns = 1: no twiddles; window folded in)
       reg_pass_first<E, P::R0, T, WIN>(a, winp, t);
       exchange<E, P::R0, T, 1, P::PADSHIFT>(a, xb, t, team);
@@ -437,7 +526,8 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
         stage_next();
         reg_pass_tw<E, P::R2, T, P::R0 * P::R1>(a, tw2, t);
       }
-      // register m now holds bin t + T*m  (.cpp:152-154)
+      }  // !HYBRID
+      // register m now holds bin P::bin_of(t, m)  (.cpp:152-154)
 #pragma unroll
       for (int m = 0; m < E; m++) {
         if constexpr (DET == DET_MAGSQ) {
@@ -458,7 +548,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       {
         float *mypart = reinterpret_cast<float *>(xb);  // N floats per team, aliasing the exchange buffer
 #pragma unroll
-        for (int m = 0; m < E; m++) mypart[t + T * m] = acc[m];
+        for (int m = 0; m < E; m++) mypart[P::bin_of(t, m)] = acc[m];
       }
       __syncthreads();
       {
@@ -508,7 +598,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
     unit_sync<T, UT>(unit);  // every thread of the unit is done reading its exchange buffer
     if (ut < T) {
 #pragma unroll
-      for (int m = 0; m < E; m++) part[t + T * m] = acc[m];
+      for (int m = 0; m < E; m++) part[P::bin_of(t, m)] = acc[m];
     }
     unit_sync<T, UT>(unit);
     {

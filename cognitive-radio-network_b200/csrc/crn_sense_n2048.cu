@@ -1,8 +1,8 @@
-// sense_kernel instantiations for N = 2048 (radix 32 x 8 x 8, 32 points per thread).
+// sense_kernel instantiations for N = 2048: hybrid plan (radix-2 across warps, then a 1024-point FFT per warp).
 #include "crn_launch.cuh"
 namespace crn {
 int launch_sense_2048(const SenseParams &prm, int window, int detector, int grid, cudaStream_t stream,
                     LaunchGeometry *geo) {
-  return launch_plan<Plan<2048, 32, 32, 8, 8, 2, 3>>(prm, window, detector, grid, stream, geo);
+  return launch_plan<HybridPlan<2048, 4, 2>>(prm, window, detector, grid, stream, geo);
 }
 }  // namespace crn
