@@ -79,8 +79,9 @@ struct Plan {
   // spectrum bin held in accumulator register m of team thread t after the last pass
   __host__ __device__ static constexpr int bin_of(int t, int m) { return t + T * m; }
   // Bulk-copy (TMA) staging of the next frame pays off where a frame spans several warps and every
-  // exchange is a multi-warp barrier (measured: +8 % at N = 4096, +13 % at N = 8192); for the one-warp-
-  // per-frame sizes plain coalesced loads plus the L2 prefetch are faster and leaner in registers.
+  // exchange is a multi-warp barrier (measured on the generic three-pass plans: +8 % at N = 4096, +13 % at
+  // N = 8192); for the one-warp-per-frame sizes plain coalesced loads plus the L2 prefetch are faster and
+  // leaner in registers (1024: 599 vs 608 GS/s in the same binary, and 684 without the staging code).
 #ifdef CRN_TMA_ALL
   static constexpr bool TMA = true;
 #else
@@ -128,7 +129,15 @@ struct HybridPlan {
   static constexpr int UNITS = TEAMS;
   static constexpr int TEAMS_PER_UNIT = 1;
   static constexpr bool HYBRID = true;
+#ifdef CRN_HYBRID_NO_TMA
   static constexpr bool TMA = false;
+#else
+  // Bulk-copy (TMA) staging of the team's next frame into its (by then idle) exchange regions: the copy
+  // flies under the last pass and the accumulate, so the next frame's first pass starts from shared memory.
+  // Measured (same binary, CRN_NO_TMA toggled): +12 % at N = 8192, +1 % at 2048; at 4096 the extra
+  // registers cost more than the staging wins (433 vs 448 GS/s), so it is compiled in for N = 8192 only.
+  static constexpr bool TMA = (N >= 8192);
+#endif
   // At N = 8192 the 32 KB window table is what keeps a second CTA off the SM; there it is read through the
   // read-only L1 path instead (the table is reused by every frame, L1 keeps it).
   static constexpr bool WIN_SMEM = (N < 8192);
@@ -505,6 +514,10 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
         __syncwarp();  // the region is rewritten in padded layout below
         reg_pass_first<E, 32, 32, false>(a, winp, lane);
         exchange<E, 32, 32, 1, 5>(a, wb, lane, 0);
+        if (tma && k + FT < K) {
+          team_sync<T>(team);  // every warp of the team has gathered its points: the regions are idle
+          if (t == 0) tma_load_frame(xb, x + fstep, frame_bytes, &mbars[team]);
+        }
         reg_pass_tw<E, 32, 32, 32>(a, tw1, lane);
       } else {
       // pass 0 (Ns = 1: no twiddles; window folded in)

@@ -143,6 +143,41 @@ def test_cuda_path_matches_oracle(crn, oracle, torch, nfft, navg, mode, L, strid
     check(crn, cfg, got, want)
 
 
+@pytest.mark.parametrize("nfft", [1024, 2048, 4096, 8192])
+def test_unaligned_buffers_and_odd_lengths(crn, oracle, torch, nfft):
+    """Frames that are only 8-byte aligned (device pointer offset by one sample) or of odd length / stride
+    cannot use 16-byte bulk copies: the kernel must fall back to plain loads and still be exact; the same
+    capture through the aligned (TMA-staged where the plan has it) path must give identical results."""
+    cfg = crn.config_welch(nfft, 5)
+    gs = cfg.group_samples
+    ng = 7
+    sc = crn.synth_config(gs, dwell_groups=1, snr_db=10.0, seed=nfft + 1)
+    iq, _ = oracle.synth(sc, ng * gs + 1)
+    want = oracle.sense_port(cfg, iq[1:])
+    stream = torch.cuda.current_stream().cuda_stream
+    d_all = torch.from_numpy(iq.view(np.float32).reshape(-1, 2)).cuda()
+    outs = []
+    for d_iq in (d_all[1:], d_all[1:].clone()):          # offset by 8 bytes, then 16-byte aligned copy
+        assert (d_iq.data_ptr() % 16 == 8) == (d_iq is not None and d_iq.data_ptr() % 16 != 0)
+        d_feat = torch.empty(ng, 4, dtype=torch.float32, device="cuda")
+        d_ann = torch.empty(ng, 3, dtype=torch.float64, device="cuda")
+        d_dec = torch.empty(ng, dtype=torch.int32, device="cuda")
+        with crn.Sensor(cfg, device=0) as s:
+            s.sense_device(d_iq, ng, d_feat, d_ann, d_dec, None, stream)
+        torch.cuda.synchronize()
+        outs.append((d_feat.cpu().numpy(), d_ann.cpu().numpy(), d_dec.cpu().numpy(), None))
+    assert d_all[1:].data_ptr() % 16 == 8
+    check(crn, cfg, outs[0], want)
+    check(crn, cfg, outs[1], want)
+    assert np.array_equal(outs[0][0], outs[1][0])
+    # odd frame length and odd stride
+    cfg2 = crn.config_welch(nfft, 3)
+    cfg2.frame_len = nfft - 37
+    cfg2.frame_stride = nfft - 37 + 2
+    iq2, _ = oracle.synth(sc, 4 * cfg2.group_samples)
+    check(crn, cfg2, run_device(crn, torch, cfg2, iq2), oracle.sense_port(cfg2, iq2))
+
+
 def test_many_groups_cover_every_cta_and_the_tail(crn, oracle, torch):
     """More groups than resident CTAs (persistent loop + ragged last wave)."""
     cfg = crn.config_welch(1024, 4)
