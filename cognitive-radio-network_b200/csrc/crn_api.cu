@@ -227,6 +227,11 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
 
   crn_handle *h = new (std::nothrow) crn_handle();
   if (!h) return crn::fail(CRN_ERR_NOMEM, "out of host memory");
+  // any early return below (CRN_CUDA) releases what was allocated so far
+  struct Guard {
+    crn_handle *h;
+    ~Guard() { if (h) crn_destroy(h); }
+  } guard{h};
   h->cfg = *cfg;
   h->device = cfg->device;
   h->stride = cfg->frame_stride > 0 ? cfg->frame_stride : cfg->frame_len;
@@ -235,7 +240,6 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   CRN_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   h->num_sms = prop.multiProcessorCount;
   if (prop.major < 10) {
-    delete h;
     return crn::fail(CRN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
                      cfg->device, prop.major, prop.minor);
   }
@@ -247,7 +251,7 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     case 2048: h->launch = crn::launch_sense_2048; break;
     case 4096: h->launch = crn::launch_sense_4096; break;
     case 8192: h->launch = crn::launch_sense_8192; break;
-    default: delete h; return crn::fail(CRN_ERR_UNSUPPORTED, "nfft %d not compiled", cfg->nfft);
+    default: return crn::fail(CRN_ERR_UNSUPPORTED, "nfft %d not compiled", cfg->nfft);
   }
 
   // tables
@@ -286,9 +290,8 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   }
 
   st = h->launch(b, cfg->window, cfg->detector, 0, nullptr, &h->geo);
-  if (st != CRN_OK) { crn_destroy(h); return st; }
+  if (st != CRN_OK) return st;
   if (h->geo.ctas_per_sm < 1) {
-    crn_destroy(h);
     return crn::fail(CRN_ERR_CUDA, "kernel %s does not fit on an SM (smem %d B)", h->geo.name, h->geo.smem_bytes);
   }
   // Epilogue strategy (crn_sense_kernel.cuh): CTA-wide when every team gets the same, long run of frames
@@ -302,7 +305,7 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     if (force && !strcmp(force, "unit")) cta = false;
     b.upg = cta ? 0 : pick_upg(h->geo.units, h->geo.teams_per_unit, cfg->navg);
     st = h->launch(b, cfg->window, cfg->detector, 0, nullptr, &h->geo);  // attributes of the chosen variant
-    if (st != CRN_OK) { crn_destroy(h); return st; }
+    if (st != CRN_OK) return st;
   }
 
   CRN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -315,9 +318,10 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     CRN_CUDA(cudaMallocHost(&s.h_iq, slot_bytes));
     CRN_CUDA(cudaMalloc(&s.d_iq, slot_bytes));
     st = alloc_results(s.res, 1, cfg->nbands);
-    if (st != CRN_OK) { crn_destroy(h); return st; }
+    if (st != CRN_OK) return st;
     CRN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }
+  guard.h = nullptr;
   *out = h;
   return CRN_OK;
 }
@@ -481,7 +485,10 @@ int crn_sense_batch_host(crn_handle *h, const float *iq, int64_t ngroups, crn_re
       memcpy(h->h_stage[b], src, n * group_bytes);
       src = h->h_stage[b];
     }
-    CRN_CUDA(cudaMemcpyAsync(h->d_stage[b], src, n * group_bytes, cudaMemcpyHostToDevice, h->stream));
+    // H2D on its own stream so the next chunk's copy overlaps this chunk's kernel and result readback
+    CRN_CUDA(cudaMemcpyAsync(h->d_stage[b], src, n * group_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CRN_CUDA(cudaEventRecord(h->stage_copied[b], h->copy_stream));
+    CRN_CUDA(cudaStreamWaitEvent(h->stream, h->stage_copied[b], 0));
     ResultBuf &r = h->stage_res[b];
     st = launch(h, h->d_stage[b], n, r.d_feat, r.d_ann, r.d_dec, r.d_mask, h->stream);
     if (st != CRN_OK) return st;
