@@ -82,11 +82,7 @@ struct Plan {
   // exchange is a multi-warp barrier (measured on the generic three-pass plans: +8 % at N = 4096, +13 % at
   // N = 8192); for the one-warp-per-frame sizes plain coalesced loads plus the L2 prefetch are faster and
   // leaner in registers (1024: 599 vs 608 GS/s in the same binary, and 684 without the staging code).
-#ifdef CRN_TMA_ALL
-  static constexpr bool TMA = true;
-#else
   static constexpr bool TMA = (T > 64);
-#endif
 #ifdef CRN_NO_PREFETCH
   static constexpr bool PREFETCH = false;
 #else
@@ -129,15 +125,11 @@ struct HybridPlan {
   static constexpr int UNITS = TEAMS;
   static constexpr int TEAMS_PER_UNIT = 1;
   static constexpr bool HYBRID = true;
-#ifdef CRN_HYBRID_NO_TMA
-  static constexpr bool TMA = false;
-#else
   // Bulk-copy (TMA) staging of the team's next frame into its (by then idle) exchange regions: the copy
   // flies under the last pass and the accumulate, so the next frame's first pass starts from shared memory.
   // Measured (same binary, CRN_NO_TMA toggled): +12 % at N = 8192, +1 % at 2048; at 4096 the extra
   // registers cost more than the staging wins (433 vs 448 GS/s), so it is compiled in for N = 8192 only.
   static constexpr bool TMA = (N >= 8192);
-#endif
   // At N = 8192 the 32 KB window table is what keeps a second CTA off the SM; there it is read through the
   // read-only L1 path instead (the table is reused by every frame, L1 keeps it).
   static constexpr bool WIN_SMEM = (N < 8192);
@@ -228,13 +220,7 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
       constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
       if constexpr (WIN) {
         const float2 w = winp[m0 * T + t];
-#ifdef CRN_NOFUSE_WIN
-        const float2 A = make_float2(a[m0].x * w.x, a[m0].y * w.x), B = make_float2(a[m0 + E / 2].x * w.y, a[m0 + E / 2].y * w.y);
-        v[br] = make_float2(A.x + B.x, A.y + B.y);
-        v[br + 1] = make_float2(A.x - B.x, A.y - B.y);
-#else
         butterfly_w_real(a[m0], a[m0 + E / 2], w.x, w.y, v[br], v[br + 1]);
-#endif
       } else {
         v[br] = make_float2(a[m0].x + a[m0 + E / 2].x, a[m0].y + a[m0 + E / 2].y);
         v[br + 1] = make_float2(a[m0].x - a[m0 + E / 2].x, a[m0].y - a[m0 + E / 2].y);
@@ -257,35 +243,18 @@ __device__ __forceinline__ void reg_pass_tw(float2 (&a)[E], const float4 *__rest
     static_for<0, R / 2>([&](auto Q) {
       constexpr int m0 = I.value + Q.value * G;
       constexpr int br = bitrev(Q.value, LOG);
-#ifdef CRN_DEBUG_NO_TW
-      const float4 w = make_float4(0.6f, 0.8f, 0.8f, -0.6f + 1e-9f * jq);  // timing experiment only
-#elif defined(CRN_TW64)
-      const float2 *twp2 = reinterpret_cast<const float2 *>(twp + Q.value * NS + jq);
-      const float2 wlo = twp2[0], whi = twp2[1];
-      const float4 w = make_float4(wlo.x, wlo.y, whi.x, whi.y);
-#else
       const float4 w = twp[Q.value * NS + jq];
-#endif
-#ifdef CRN_NOFUSE_TW
-      const float2 A = (Q.value == 0) ? a[m0] : cmul(a[m0], make_float2(w.x, w.y));
-      const float2 B = cmul(a[m0 + E / 2], make_float2(w.z, w.w));
-      v[br] = make_float2(A.x + B.x, A.y + B.y);
-      v[br + 1] = make_float2(A.x - B.x, A.y - B.y);
-#else
       butterfly_w_cplx<Q.value == 0>(a[m0], a[m0 + E / 2], make_float2(w.x, w.y), make_float2(w.z, w.w),
                                      v[br], v[br + 1]);
-#endif
     });
     fft_dit<R, 2>(v);
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
 }
 
-#ifdef CRN_X64
-#define CRN_XPAD 1  // 8-byte exchange stores: one pad slot per row is conflict-free
-#else
-#define CRN_XPAD 2  // 16-byte exchange stores need 16-byte aligned rows
-#endif
+// Exchange rows are padded by two points: rows stay 16-byte aligned for the 16-byte stores of pass 0 and
+// consecutive rows land in different banks (row stride 34 or 18 points -> conflict-free quarter-warps).
+#define CRN_XPAD 2
 // DIF twiddles of the hybrid plan: register i + r*G holds z_r[n] with n = t + T*i; multiply by W_N^(n r).
 // Only W_N^n comes from the table; the powers are built by squaring / one multiplication each.
 template <int E, int C, int T>
@@ -316,11 +285,7 @@ __device__ __forceinline__ void exchange(float2 (&a)[E], float2 *__restrict__ xb
   team_sync<T>(team);  // previous readers of xb are done
   static_for<0, G>([&](auto I) {
     const int j = t + T * I.value;
-#ifdef CRN_X64
-    if constexpr (false) {
-#else
     if constexpr (NS == 1 && R == (1 << PADSHIFT)) {
-#endif
       // pass 0: this thread owns one padded row of R consecutive points -> 16-byte stores
       float4 *row = reinterpret_cast<float4 *>(xb + j * (R + CRN_XPAD));
       static_for<0, R / 2>([&](auto Q) {
@@ -343,34 +308,32 @@ __device__ __forceinline__ void unit_sync(int unit) {
 }
 
 // MLP + first-match chain (or energy detector) for one decision, run by one warp; `fb` holds the features.
+// The MLP (.cpp:200,214-235: double precision, logistic units, bias at index 0) is spread over lanes - hidden
+// unit j on lane j, output k on lane k - so the warp pays for two dependent exp() instead of eight; every
+// unit still sums in the reference's order, so the outputs are those of the serial loop bit for bit.
 __device__ __forceinline__ void decide_and_store(const SenseParams &prm, const float *fb, long long g, int lane) {
   if (prm.decide == CRN_DECIDE_ANN) {
+    const int j = (lane >= 1 && lane <= CRN_ANN_HIDDEN) ? lane : 1;
+    double sum = prm.wih[0][j];
+#pragma unroll
+    for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += (double)fb[i - 1] * prm.wih[i][j];
+    const double Hj = 1.0 / (1.0 + exp(-sum));  // Sigmoid_HA[j], valid on lanes 1..5
+    const int k = (lane >= 1 && lane <= CRN_ANN_OUTPUTS) ? lane : 1;
+    double so = prm.who[0][k];
+#pragma unroll
+    for (int jj = 1; jj <= CRN_ANN_HIDDEN; jj++) so += __shfl_sync(0xffffffffu, Hj, jj) * prm.who[jj][k];
+    const double ok = 1.0 / (1.0 + exp(-so));    // Output[k], valid on lanes 1..3
+    const double o1 = __shfl_sync(0xffffffffu, ok, 1), o2 = __shfl_sync(0xffffffffu, ok, 2),
+                 o3 = __shfl_sync(0xffffffffu, ok, 3);
     if (lane == 0) {
-      // .cpp:200,214-235: double-precision 4-5-3 logistic MLP, bias at index 0
-      double H[CRN_ANN_HIDDEN + 1];
-#pragma unroll
-      for (int j = 1; j <= CRN_ANN_HIDDEN; j++) {
-        double sum = prm.wih[0][j];
-#pragma unroll
-        for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += (double)fb[i - 1] * prm.wih[i][j];
-        H[j] = 1.0 / (1.0 + exp(-sum));
-      }
-      double out[CRN_ANN_OUTPUTS + 1];
-#pragma unroll
-      for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) {
-        double sum = prm.who[0][k];
-#pragma unroll
-        for (int j = 1; j <= CRN_ANN_HIDDEN; j++) sum += H[j] * prm.who[j][k];
-        out[k] = 1.0 / (1.0 + exp(-sum));
-      }
       int dec = CRN_ALL_BUSY;  // .cpp:245-261
-      if (out[1] >= prm.threshold) dec = CRN_CH1_OCCUPIED;
-      else if (out[2] >= prm.threshold) dec = CRN_CH2_OCCUPIED;
-      else if (out[3] >= prm.threshold) dec = CRN_CH3_OCCUPIED;
+      if (o1 >= prm.threshold) dec = CRN_CH1_OCCUPIED;
+      else if (o2 >= prm.threshold) dec = CRN_CH2_OCCUPIED;
+      else if (o3 >= prm.threshold) dec = CRN_CH3_OCCUPIED;
       if (prm.ann) {
-        prm.ann[3 * g + 0] = out[1];
-        prm.ann[3 * g + 1] = out[2];
-        prm.ann[3 * g + 2] = out[3];
+        prm.ann[3 * g + 0] = o1;
+        prm.ann[3 * g + 1] = o2;
+        prm.ann[3 * g + 2] = o3;
       }
       if (prm.decision) prm.decision[g] = dec;
       if (prm.mask) prm.mask[g] = dec ? (1ull << (dec - 1)) : 0ull;
@@ -461,9 +424,6 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
 
   int it = 0;
   for (long long g = (long long)blockIdx.x * GL + gl; g < prm.ngroups; g += gstep, it++) {
-#ifdef CRN_ALIGN_GROUPS
-    __syncthreads();  // experiment: re-align the CTA's warps at every group (valid when upg == UNITS)
-#endif
     float acc[E];
 #pragma unroll
     for (int m = 0; m < E; m++) acc[m] = 0.0f;
@@ -567,15 +527,29 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       {
         const int warp = tid >> 5, lane = tid & 31;
         constexpr int NW = NT / 32;
-        for (int s = warp; s < prm.nsegs; s += NW) {
-          float sum = 0.0f;
-          for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) {
+        // four segments per trip so their loads and shuffle trees overlap instead of queueing up
+        for (int sb = warp; sb < prm.nsegs; sb += 4 * NW) {
+          float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int q = 0; q < TEAMS; q++) sum += reinterpret_cast<const float *>(xbuf + (size_t)q * P::XSZ)[i];
+          for (int u = 0; u < 4; u++) {
+            const int s = sb + u * NW;
+            if (s < prm.nsegs)
+              for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) {
+#pragma unroll
+                for (int q = 0; q < TEAMS; q++)
+                  sum[u] += reinterpret_cast<const float *>(xbuf + (size_t)q * P::XSZ)[i];
+              }
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) segsum[s] = sum;
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              if (sb + u * NW < prm.nsegs) segsum[sb + u * NW] = sum[u];
+          }
         }
       }
       __syncthreads();
@@ -624,12 +598,24 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       }
       __syncwarp();
       float *mine = segpart + ((size_t)slot * UNITS + unit) * CRN_MAX_SEGS;
-      for (int s = wu; s < prm.nsegs; s += NWU) {
-        float sum = 0.0f;
-        for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) sum += part[i];
+      for (int sb = wu; sb < prm.nsegs; sb += 4 * NWU) {  // four segments per trip (independent chains)
+        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) mine[s] = sum;
+        for (int u = 0; u < 4; u++) {
+          const int s = sb + u * NWU;
+          if (s < prm.nsegs)
+            for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) sum[u] += part[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (sb + u * NWU < prm.nsegs) mine[sb + u * NWU] = sum[u];
+        }
       }
     }
     unit_sync<T, UT>(unit);  // partial sums written, `part` free again
