@@ -50,6 +50,7 @@ WORKLOADS = {
     "config2": WORKLOAD,
     "wideband": "configs[2]: wideband sweep, 8192-pt FFT, 64 equal sub-channels, 100 MHz equivalent rate, energy-detection features, 64-frame average, 1e9 complex-float samples",
     "multiradio": "configs[3]: multi-radio, 4096 independent sensing streams (simulated CORNET nodes), 2048-pt FFT, 64-frame Welch average + ANN, one decision per stream (537e6 samples)",
+    "sc16": "configs[1] fed in the USRP wire format: 1024-pt FFT, Hann, 64-frame Welch average + ANN, 1e9 samples as int16 (I,Q) pairs (4 B/sample), converted on the GPU",
     "refexact": "configs[0] on the GPU: reference-exact mode, 512-pt FFT, no window, |X| averaged over 10 frames, (sum)^2 features + ANN, 1e9 complex-float samples",
 }
 ACTIVE = {"name": "config2"}
@@ -69,6 +70,8 @@ def workload_config(crn):
         cfg = crn.config_reference()
         return cfg, TOTAL_SAMPLES // cfg.group_samples
     cfg = crn.config_welch(NFFT, NAVG)
+    if w == "sc16":
+        cfg.iq_format = crn.IQ_SC16
     return cfg, TOTAL_SAMPLES // cfg.group_samples  # 15258 full decisions, remainder dropped
 
 
@@ -197,13 +200,14 @@ def cpu_leg(crn, cfg, iq_host, budget_s, threads=None):
     oracle = _oracle()
     nthreads = threads or oracle.port().crn_oracle_max_threads()
     gs = cfg.group_samples
-    have = iq_host.size // gs
+    eps = 2 if cfg.iq_format == crn.IQ_SC16 else 1   # array elements per sample (int16 pairs vs complex64)
+    have = iq_host.size // (gs * eps)
     probe = min(have, max(4 * nthreads, 32))
-    t = oracle.time_port(cfg, iq_host[: probe * gs], probe, nthreads)
+    t = oracle.time_port(cfg, iq_host[: probe * gs * eps], probe, nthreads)
     rate = probe * gs / max(t, 1e-9)
     n = int(min(have, max(probe, rate * budget_s // gs)))
     passes = max(1, int(round(budget_s / (n * gs / rate))))
-    secs = sum(oracle.time_port(cfg, iq_host[: n * gs], n, nthreads) for _ in range(passes))
+    secs = sum(oracle.time_port(cfg, iq_host[: n * gs * eps], n, nthreads) for _ in range(passes))
     return {"value": passes * n * gs / secs / 1e9, "unit": UNIT, "cores": nthreads, "kind": "port",
             "sample": "%d pass(es) over the first %d of %d decision groups (%d samples per pass) of the same synthetic "
                       "capture, %.1f s of CPU work on %d threads; reference algorithm restated in C (oracle/crn_oracle.c, "
@@ -299,6 +303,15 @@ def run_ours(args):
         crn.synth_generate_streams(synth_cfg(crn, cfg), d_iq, rank * ngroups, ngroups, gs, d_state, local_rank, stream)
     else:
         crn.synth_generate(synth_cfg(crn, cfg), d_iq, rank * nsamp, nsamp, d_state, local_rank, stream)
+    sample_bytes = 8
+    if cfg.iq_format == crn.IQ_SC16:   # quantise the capture to the 16-bit wire format, in place chunks
+        sample_bytes = 4
+        d16 = torch.empty(nsamp, 2, dtype=torch.int16, device=dev)
+        step_q = 1 << 26
+        for i0 in range(0, nsamp, step_q):
+            d16[i0:i0 + step_q] = (d_iq[i0:i0 + step_q] * 32768.0).round_().clamp_(-32768, 32767).to(torch.int16)
+        d_iq = d16
+        torch.cuda.synchronize()
     d_feat = torch.empty(ngroups, cfg.nbands, dtype=torch.float32, device=dev)
     d_ann = torch.empty(ngroups, 3, dtype=torch.float64, device=dev)
     d_dec = torch.empty(ngroups, dtype=torch.int32, device=dev)
@@ -333,7 +346,10 @@ def run_ours(args):
 
     # ---- parity spot check of this very batch against the oracle (outside every timed region) ----------
     pick = sorted(set([0, ngroups // 2, ngroups - 1]))
-    iq_pick = np.concatenate([d_iq[g * gs:(g + 1) * gs].cpu().numpy().view(np.complex64).ravel() for g in pick])
+    if cfg.iq_format == crn.IQ_SC16:
+        iq_pick = np.concatenate([d_iq[g * gs:(g + 1) * gs].cpu().numpy().ravel() for g in pick])
+    else:
+        iq_pick = np.concatenate([d_iq[g * gs:(g + 1) * gs].cpu().numpy().view(np.complex64).ravel() for g in pick])
     oracle = _oracle()
     of, oa, od, _ = oracle.sense_port(cfg, iq_pick)
     gf, ga, gd = d_feat.cpu().numpy()[pick], d_ann.cpu().numpy()[pick], d_dec.cpu().numpy()[pick]
@@ -347,7 +363,7 @@ def run_ours(args):
     # ---- end to end through the C-ABI host path: pinned host IQ -> H2D -> kernel -> D2H results --------
     e2e = None
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h_iq = torch.empty(nsamp, 2, dtype=torch.float32, pin_memory=True)
+    h_iq = torch.empty(nsamp, 2, dtype=d_iq.dtype, pin_memory=True)
     h_iq.copy_(d_iq)
     torch.cuda.synchronize()
     res = (crn.Result * ngroups)()
@@ -363,7 +379,7 @@ def run_ours(args):
     hf, ha, hd, _ = crn.results_to_arrays(res, cfg.nbands)
     e2e_ok = bool(np.array_equal(hf, d_feat.cpu().numpy()) and np.array_equal(hd, d_dec.cpu().numpy()))
     e2e = {"value": world * nsamp * e2e_steps / e2e_sec / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": nsamp * 8, "d2h_bytes_per_step": ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8),
+           "h2d_bytes_per_step": nsamp * sample_bytes, "d2h_bytes_per_step": ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8),
            "steps": e2e_steps, "path": "crn_sense_batch_host (C-ABI), pinned host IQ, 64 MiB double-buffered chunks; wall clock, max over ranks",
            "matches_device_path": e2e_ok}
 
@@ -375,15 +391,15 @@ def run_ours(args):
     # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same capture -----------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        iq_host = h_iq.numpy().view(np.complex64).ravel()
+        iq_host = h_iq.numpy().ravel() if cfg.iq_format == crn.IQ_SC16 else h_iq.numpy().view(np.complex64).ravel()
         cpu = cpu_leg(crn, cfg, iq_host, args.cpu_seconds)
     peak, peak_src = measured_peak()
     kernel_ms = sum(step_ms) / len(step_ms)  # one launch per step: event-timed launch duration
-    achieved = nsamp * 8 / (kernel_ms * 1e-3) / 1e9
+    achieved = nsamp * sample_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": profiled_traffic(), "kernel": info["name"], "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": nsamp * 8, "kernel_ms": kernel_ms,
-                "note": "8 B per complex sample read once; feature write-back (%d B per launch) not counted" %
+                "algorithmic_bytes_per_launch": nsamp * sample_bytes, "kernel_ms": kernel_ms,
+                "note": "%d B per complex sample read once;" % sample_bytes + " feature write-back (%d B per launch) not counted" %
                         (ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8))}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,

@@ -27,6 +27,7 @@ DET_MAG, DET_MAGSQ = 0, 1
 POST_SQUARE_OF_SUM, POST_SUM = 0, 1
 DECIDE_NONE, DECIDE_ANN, DECIDE_ENERGY = 0, 1, 2
 ALL_BUSY, CH1_OCCUPIED, CH2_OCCUPIED, CH3_OCCUPIED = 0, 1, 2, 3
+IQ_CF32, IQ_SC16 = 0, 1
 
 # TX retune the reference performs for each decision (CE_Predictive_Node.cpp:245-261, .hpp:55-57)
 TX_FREQ_FOR_DECISION = {ALL_BUSY: None, CH1_OCCUPIED: 835e6, CH2_OCCUPIED: 833e6, CH3_OCCUPIED: 835e6}
@@ -46,6 +47,7 @@ class Config(C.Structure):
         ("ann_who", (C.c_double * 4) * 6),
         ("ann_threshold", C.c_double), ("energy_factor", C.c_double),
         ("device", C.c_int32), ("ring_slots", C.c_int32),
+        ("iq_format", C.c_int32), ("reserved_", C.c_int32),
     ]
 
     def copy(self):
@@ -95,7 +97,7 @@ API = {
     "crn_config_validate": (C.c_int, [C.POINTER(Config)]),
     "crn_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "crn_destroy": (C.c_int, [_P]),
-    "crn_ring_acquire": (C.c_int, [_P, C.POINTER(C.POINTER(C.c_float))]),
+    "crn_ring_acquire": (C.c_int, [_P, C.POINTER(_P)]),
     "crn_submit": (C.c_int, [_P, C.c_int32]),
     "crn_poll": (C.c_int, [_P, C.POINTER(Result)]),
     "crn_wait": (C.c_int, [_P, C.POINTER(Result)]),
@@ -225,12 +227,17 @@ class Sensor:
     def push_frame(self, frame):
         """Copy one frame of L complex64 samples into the pinned ring and commit it."""
         L = self.cfg.frame_len
-        fr = np.ascontiguousarray(frame, dtype=np.complex64)
-        if fr.shape != (L,):
-            raise ValueError("frame must hold exactly frame_len=%d complex samples" % L)
-        slot = C.POINTER(C.c_float)()
+        if self.cfg.iq_format == IQ_SC16:
+            fr = np.ascontiguousarray(frame, dtype=np.int16).reshape(-1)
+            if fr.shape != (2 * L,):
+                raise ValueError("frame must hold exactly frame_len=%d (I,Q) int16 pairs" % L)
+        else:
+            fr = np.ascontiguousarray(frame, dtype=np.complex64)
+            if fr.shape != (L,):
+                raise ValueError("frame must hold exactly frame_len=%d complex samples" % L)
+        slot = _P()
         _check(lib.crn_ring_acquire(self._h, C.byref(slot)), "crn_ring_acquire")
-        C.memmove(slot, fr.ctypes.data, 8 * L)
+        C.memmove(slot, fr.ctypes.data, fr.nbytes)
         _check(lib.crn_submit(self._h, 1), "crn_submit")
 
     def poll(self):
@@ -257,6 +264,10 @@ class Sensor:
         if hasattr(iq, "data_ptr"):
             nsamp = iq.numel() // (1 if iq.is_complex() else 2)
             ptr = C.c_void_p(iq.data_ptr())
+        elif self.cfg.iq_format == IQ_SC16:
+            iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+            nsamp = iq.size // 2
+            ptr = C.c_void_p(iq.ctypes.data)
         else:
             iq = np.ascontiguousarray(iq, dtype=np.complex64)
             nsamp = iq.size

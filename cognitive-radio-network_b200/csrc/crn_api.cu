@@ -36,8 +36,8 @@ struct ResultBuf {
 };
 
 struct RingSlot {
-  float *h_iq = nullptr;   // pinned [K][L] complex
-  float2 *d_iq = nullptr;  // device mirror
+  unsigned char *h_iq = nullptr;  // pinned [K][L] samples in cfg.iq_format
+  unsigned char *d_iq = nullptr;  // device mirror
   ResultBuf res;
   cudaEvent_t done = nullptr;
   uint64_t first_frame = 0;
@@ -51,6 +51,7 @@ struct crn_handle {
   int device = 0;
   int num_sms = 0;
   int stride = 0;
+  size_t sample_bytes = 8;  // 8 (CF32) or 4 (SC16)
   crn::sense_launch_fn launch = nullptr;
   crn::LaunchGeometry geo;
   crn::SenseParams base;  // everything but iq / outputs / ngroups
@@ -66,8 +67,8 @@ struct crn_handle {
   uint64_t frames_seen = 0;
   // batch-host staging (double buffered)
   int64_t chunk_groups = 0;
-  float *h_stage[2] = {nullptr, nullptr};
-  float2 *d_stage[2] = {nullptr, nullptr};
+  unsigned char *h_stage[2] = {nullptr, nullptr};
+  unsigned char *d_stage[2] = {nullptr, nullptr};
   ResultBuf stage_res[2];
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
   cudaEvent_t stage_copied[2] = {nullptr, nullptr};
@@ -181,11 +182,11 @@ int grid_for(const crn_handle *h, int64_t ngroups) {
   return (int)(g < 1 ? 1 : g);
 }
 
-int launch(crn_handle *h, const float2 *d_iq, int64_t ngroups, float *d_feat, double *d_ann,
+int launch(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat, double *d_ann,
            int32_t *d_dec, unsigned long long *d_mask, cudaStream_t s) {
   if (ngroups <= 0) return CRN_OK;
   crn::SenseParams p = h->base;
-  p.iq = d_iq;
+  p.iq = static_cast<const float2 *>(d_iq);
   p.feat = d_feat;
   p.ann = d_ann;
   p.decision = d_dec;
@@ -194,7 +195,7 @@ int launch(crn_handle *h, const float2 *d_iq, int64_t ngroups, float *d_feat, do
   // bulk-copy (TMA) staging needs 16-byte aligned frame addresses and sizes; anything else uses plain loads
   const char *no_tma = getenv("CRN_NO_TMA");
   p.use_tma = (p.upg == 0) && !(no_tma && no_tma[0] == '1') && ((reinterpret_cast<uintptr_t>(d_iq) & 15) == 0) &&
-              (h->stride % 2 == 0) && (h->cfg.frame_len % 2 == 0);
+              ((h->stride * h->sample_bytes) % 16 == 0) && ((h->cfg.frame_len * h->sample_bytes) % 16 == 0);
   int st = h->launch(p, h->cfg.window, h->cfg.detector, grid_for(h, ngroups), s, nullptr);
   if (st == CRN_OK) h->launches++;
   return st;
@@ -235,6 +236,7 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   h->cfg = *cfg;
   h->device = cfg->device;
   h->stride = cfg->frame_stride > 0 ? cfg->frame_stride : cfg->frame_len;
+  h->sample_bytes = cfg->iq_format == CRN_IQ_SC16 ? 4 : 8;
   if (h->cfg.ring_slots == 0) h->cfg.ring_slots = 4;
   cudaDeviceProp prop;
   CRN_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -274,7 +276,13 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   b.L = cfg->frame_len;
   b.stride = h->stride;
   b.K = cfg->navg;
-  b.invK = 1.0f / (float)cfg->navg;
+  // sc16 samples are converted to float unscaled (exact); their 1/32768 (or its square for |X|^2) rides on 1/K
+  {
+    double scale = 1.0 / (double)cfg->navg;
+    if (cfg->iq_format == CRN_IQ_SC16) scale *= (cfg->detector == CRN_DET_MAGSQ) ? (1.0 / 32768.0) * (1.0 / 32768.0) : (1.0 / 32768.0);
+    b.invK = (float)scale;
+    b.sc16 = cfg->iq_format == CRN_IQ_SC16;
+  }
   b.nbands = cfg->nbands;
   b.nsegs = cfg->nsegs;
   b.postop = cfg->postop;
@@ -312,7 +320,7 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   CRN_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 
   // streaming ring: ring_slots decisions of K frames each
-  const size_t slot_bytes = sizeof(float) * 2 * (size_t)cfg->navg * cfg->frame_len;
+  const size_t slot_bytes = h->sample_bytes * (size_t)cfg->navg * cfg->frame_len;
   h->ring.resize(h->cfg.ring_slots);
   for (auto &s : h->ring) {
     CRN_CUDA(cudaMallocHost(&s.h_iq, slot_bytes));
@@ -354,11 +362,11 @@ int crn_destroy(crn_handle *h) {
 
 // ---- streaming path -------------------------------------------------------------------------------
 
-int crn_ring_acquire(crn_handle *h, float **slot) {
+int crn_ring_acquire(crn_handle *h, void **slot) {
   if (!h || !slot) return crn::fail(CRN_ERR_INVALID, "crn_ring_acquire: null argument");
   RingSlot &s = h->ring[h->fill_slot];
   if (s.state != 0) return crn::fail(CRN_ERR_OVERRUN, "ring full: %d decisions unread", h->inflight);
-  *slot = s.h_iq + 2 * (size_t)h->fill_frames * h->cfg.frame_len;
+  *slot = s.h_iq + h->sample_bytes * (size_t)h->fill_frames * h->cfg.frame_len;
   return CRN_OK;
 }
 
@@ -374,11 +382,11 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   if (h->fill_frames < h->cfg.navg) return CRN_OK;
   // K-th frame: ship the slot and enqueue the fused kernel (stream ordered, non blocking)
   CRN_CUDA(cudaSetDevice(h->device));
-  const size_t slot_bytes = sizeof(float) * 2 * (size_t)h->cfg.navg * h->cfg.frame_len;
+  const size_t slot_bytes = h->sample_bytes * (size_t)h->cfg.navg * h->cfg.frame_len;
   CRN_CUDA(cudaMemcpyAsync(s.d_iq, s.h_iq, slot_bytes, cudaMemcpyHostToDevice, h->stream));
   crn::SenseParams p = h->base;
   p.stride = h->cfg.frame_len;  // ring slots are packed
-  p.iq = s.d_iq;
+  p.iq = reinterpret_cast<const float2 *>(s.d_iq);
   p.feat = s.res.d_feat;
   p.ann = s.res.d_ann;
   p.decision = s.res.d_dec;
@@ -430,17 +438,17 @@ int crn_sense_batch_device(crn_handle *h, const void *d_iq, int64_t ngroups, flo
   if (!h || !d_iq || !d_feat || ngroups < 0)
     return crn::fail(CRN_ERR_INVALID, "crn_sense_batch_device: bad argument");
   CRN_CUDA(cudaSetDevice(h->device));
-  return launch(h, (const float2 *)d_iq, ngroups, d_feat, d_ann, d_decision,
+  return launch(h, d_iq, ngroups, d_feat, d_ann, d_decision,
                 (unsigned long long *)d_mask, (cudaStream_t)cuda_stream);
 }
 
-int crn_sense_batch_host(crn_handle *h, const float *iq, int64_t ngroups, crn_result *results) {
+int crn_sense_batch_host(crn_handle *h, const void *iq_, int64_t ngroups, crn_result *results) {
+  const unsigned char *iq = static_cast<const unsigned char *>(iq_);
   if (!h || !iq || !results || ngroups < 0)
     return crn::fail(CRN_ERR_INVALID, "crn_sense_batch_host: bad argument");
   if (ngroups == 0) return CRN_OK;
   CRN_CUDA(cudaSetDevice(h->device));
-  const size_t group_floats = 2 * (size_t)h->stride * h->cfg.navg;
-  const size_t group_bytes = group_floats * sizeof(float);
+  const size_t group_bytes = h->sample_bytes * (size_t)h->stride * h->cfg.navg;
   if (h->chunk_groups == 0) {
     // ~64 MiB chunks: large enough to amortise launch + copy latency, small enough to overlap
     int64_t cg = (int64_t)((64u << 20) / group_bytes);
@@ -480,7 +488,7 @@ int crn_sense_batch_host(crn_handle *h, const float *iq, int64_t ngroups, crn_re
     if (st != CRN_OK) return st;
     const int64_t g0 = c * cg;
     const int64_t n = (ngroups - g0 < cg) ? (ngroups - g0) : cg;
-    const float *src = iq + g0 * group_floats;
+    const unsigned char *src = iq + g0 * group_bytes;
     if (!pinned) {
       memcpy(h->h_stage[b], src, n * group_bytes);
       src = h->h_stage[b];

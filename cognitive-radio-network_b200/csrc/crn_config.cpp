@@ -75,6 +75,7 @@ int crn_config_reference(crn_config *c) {
   c->energy_factor = 4.0;
   c->device = 0;
   c->ring_slots = 4;
+  c->iq_format = CRN_IQ_CF32;
   return CRN_OK;
 }
 
@@ -151,6 +152,7 @@ int crn_config_validate(const crn_config *c) {
       return crn::fail(CRN_ERR_INVALID, "segment out of range");
   }
   if (c->ring_slots != 0 && c->ring_slots < 2) return crn::fail(CRN_ERR_INVALID, "ring_slots must be >= 2");
+  if (c->iq_format != CRN_IQ_CF32 && c->iq_format != CRN_IQ_SC16) return crn::fail(CRN_ERR_INVALID, "unknown iq_format");
   return CRN_OK;
 }
 

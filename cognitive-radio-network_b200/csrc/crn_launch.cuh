@@ -22,9 +22,9 @@ struct LaunchGeometry {
 typedef int (*sense_launch_fn)(const SenseParams &prm, int window, int detector, int grid,
                                cudaStream_t stream, LaunchGeometry *geo_only);
 
-template <class P, bool WIN, int DET, int EPI>
-int launch_epi(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
-  auto kern = sense_kernel<P, WIN, DET, EPI>;
+template <class P, bool WIN, int DET, int EPI, bool SC16>
+int launch_fmt(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
+  auto kern = sense_kernel<P, WIN, DET, EPI, SC16>;
   const size_t smem = P::smem_bytes(WIN);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
@@ -44,14 +44,21 @@ int launch_epi(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeom
     geo->teams = P::TEAMS;
     geo->units = P::UNITS;
     geo->teams_per_unit = P::TEAMS_PER_UNIT;
-    snprintf(geo->name, sizeof(geo->name), "sense_n%d_r%dx%dx%d_%s_%s_%s", P::N, P::R0, P::R1, P::R2,
-             WIN ? "hann" : "rect", DET == DET_MAGSQ ? "magsq" : "mag", EPI == EPI_CTA ? "cta" : "unit");
+    snprintf(geo->name, sizeof(geo->name), "sense_n%d_r%dx%dx%d_%s_%s_%s%s", P::N, P::R0, P::R1, P::R2,
+             WIN ? "hann" : "rect", DET == DET_MAGSQ ? "magsq" : "mag", EPI == EPI_CTA ? "cta" : "unit",
+             SC16 ? "_sc16" : "");
     return CRN_OK;
   }
   kern<<<grid, P::NT, smem, stream>>>(prm);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "sense kernel launch: %s", cudaGetErrorString(e));
   return CRN_OK;
+}
+
+template <class P, bool WIN, int DET, int EPI>
+int launch_epi(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
+  return prm.sc16 ? launch_fmt<P, WIN, DET, EPI, true>(prm, grid, stream, geo)
+                  : launch_fmt<P, WIN, DET, EPI, false>(prm, grid, stream, geo);
 }
 
 // prm.upg == 0 selects the CTA-wide epilogue, > 0 the unit epilogue with that many units per group.

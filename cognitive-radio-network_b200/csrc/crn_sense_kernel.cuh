@@ -31,6 +31,7 @@
 // decision while the others already work on their next group.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 
 #include "crn_fft_regs.cuh"
 #include "crnsense.h"
@@ -53,6 +54,7 @@ struct SenseParams {
   int nbands, nsegs, postop, decide;
   int upg;               // reduction units per decision group (divides UNITS); 0 = CTA-wide epilogue
   int use_tma;           // 1: stage frames with cp.async.bulk (needs 16-byte aligned frames, CTA epilogue)
+  int sc16;              // IQ buffers hold int16 pairs (4 B/sample) instead of float pairs
   double threshold, energy_factor;
   double wih[CRN_ANN_INPUTS + 1][CRN_ANN_HIDDEN + 1];
   double who[CRN_ANN_HIDDEN + 1][CRN_ANN_OUTPUTS + 1];
@@ -152,12 +154,24 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
 }
+// sc16 wire format: one 32-bit word = (I, Q) as int16.  The conversion is exact (|v| <= 32768 fits fp32);
+// the 1/32768 scale is applied once to the finished features (folded into invK by the host).
+__device__ __forceinline__ float2 unpack_sc16(unsigned v) {
+  return make_float2((float)(short)(v & 0xffffu), (float)(short)(v >> 16));
+}
+__device__ __forceinline__ float2 ld_stream(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return unpack_sc16(v);
+}
+__device__ __forceinline__ float2 ld_staged(const float2 *p) { return *p; }
+__device__ __forceinline__ float2 ld_staged(const unsigned *p) { return unpack_sc16(*p); }
 
 // Pull one frame (E*T*8 bytes, 128-byte lines) towards L2 ahead of use: lane t touches lines t + T*i.
 // `line` points at this thread's first line (frame + 128 t bytes); `bytes_left` = frame bytes beyond it.
-template <int E, int T>
-__device__ __forceinline__ void prefetch_frame_l2(const float2 *line, int bytes_left) {
-  constexpr int LINES_PER_THREAD = (E + 15) / 16;  // E*T*8/128 lines over T threads
+template <int E, int T, typename S>
+__device__ __forceinline__ void prefetch_frame_l2(const S *line, int bytes_left) {
+  constexpr int LINES_PER_THREAD = (E * (int)sizeof(S) + 127) / 128;  // E*T*sizeof(S)/128 lines over T threads
 #pragma unroll
   for (int i = 0; i < LINES_PER_THREAD; i++) {
     if (128 * T * i < bytes_left)
@@ -369,8 +383,11 @@ __device__ __forceinline__ void decide_and_store(const SenseParams &prm, const f
 //              warp busy when groups are short (reference mode: K = 10) or K does not divide by TEAMS.
 enum { EPI_CTA = 0, EPI_UNIT = 1 };
 
-template <class P, bool WIN, int DET, int EPI>
+template <class P, bool WIN, int DET, int EPI, bool SC16>
 __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams prm) {
+  using sample_t = typename std::conditional<SC16, unsigned, float2>::type;  // one IQ sample in memory
+  constexpr int SPL = 128 / (int)sizeof(sample_t);                           // samples per 128-byte line
+  const sample_t *const iq = reinterpret_cast<const sample_t *>(prm.iq);
   constexpr int N = P::N, E = P::E, T = P::T, TEAMS = P::TEAMS, NT = P::NT;
   constexpr int UT = P::UNIT_THREADS, UNITS = P::UNITS, TPU = P::TEAMS_PER_UNIT;
   constexpr bool PREFETCH = P::PREFETCH;
@@ -416,10 +433,10 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
   const int L = prm.L, K = prm.K;
   const bool full = (L == N);
   const long long gstep = (long long)gridDim.x * GL;
-  const unsigned frame_bytes = (unsigned)L * 8u;
+  const unsigned frame_bytes = (unsigned)L * (unsigned)sizeof(sample_t);
   unsigned tma_phase = 0;
   if (tma && t == 0 && fs < K && (long long)blockIdx.x * GL + gl < prm.ngroups)  // first frame of the first group
-    tma_load_frame(xb, prm.iq + (((size_t)blockIdx.x * GL + gl) * (size_t)K + (size_t)fs) * (size_t)prm.stride,
+    tma_load_frame(xb, iq + (((size_t)blockIdx.x * GL + gl) * (size_t)K + (size_t)fs) * (size_t)prm.stride,
                    frame_bytes, &mbars[team]);
 
   int it = 0;
@@ -430,16 +447,17 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
 
     // frame pointers advance by plain 64-bit adds inside the loop; the multiplications happen once per group
     const size_t fstep = (size_t)FT * (size_t)prm.stride;  // samples between this team's frames
-    const float2 *x = prm.iq + ((size_t)g * (size_t)K + (size_t)fs) * (size_t)prm.stride + t;
+    const sample_t *x = iq + ((size_t)g * (size_t)K + (size_t)fs) * (size_t)prm.stride + t;
     // first frame this team senses in the CTA's next group (prefetch target at the group boundary);
-    // "+ 15 t" turns the per-thread sample pointer into a per-thread 128-byte line pointer (16 samples/line)
-    const float2 *xng = (g + gstep < prm.ngroups) ? x + (size_t)gstep * (size_t)K * (size_t)prm.stride + 15 * t : nullptr;
+    // "+ (SPL-1) t" turns the per-thread sample pointer into a per-thread 128-byte line pointer
+    const sample_t *xng =
+        (g + gstep < prm.ngroups) ? x + (size_t)gstep * (size_t)K * (size_t)prm.stride + (SPL - 1) * t : nullptr;
     for (int k = fs; k < K; k += FT, x += fstep) {
       if constexpr (PREFETCH) {
         // the frame this team senses next: k + FT of this group, else its first frame of the next
         // group.  One frame of compute covers the DRAM latency, so the loads below hit L2.
-        const float2 *nx = (k + FT < K) ? x + fstep + 15 * t : xng;
-        if (nx) prefetch_frame_l2<E, T>(nx, L * 8 - 128 * t);
+        const sample_t *nx = (k + FT < K) ? x + fstep + (SPL - 1) * t : xng;
+        if (nx) prefetch_frame_l2<E, T>(nx, (int)frame_bytes - 128 * t);
       }
       float2 a[E];
       if (tma) {
@@ -447,7 +465,9 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
         mbar_wait(&mbars[team], tma_phase);
         tma_phase ^= 1u;
 #pragma unroll
-        for (int m = 0; m < E; m++) a[m] = (full || t + T * m < L) ? xb[t + T * m] : make_float2(0.f, 0.f);
+        for (int m = 0; m < E; m++)
+          a[m] = (full || t + T * m < L) ? ld_staged(reinterpret_cast<const sample_t *>(xb) + t + T * m)
+                                         : make_float2(0.f, 0.f);
       } else if (full) {
 #pragma unroll
         for (int m = 0; m < E; m++) a[m] = ld_stream(x + T * m);
@@ -568,7 +588,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       }
       // the exchange buffers are free again (the last barrier above): pull the first frame of the next group
       if (tma && t == 0 && fs < K && g + gstep < prm.ngroups)
-        tma_load_frame(xb, prm.iq + ((size_t)(g + gstep) * (size_t)K + (size_t)fs) * (size_t)prm.stride,
+        tma_load_frame(xb, iq + ((size_t)(g + gstep) * (size_t)K + (size_t)fs) * (size_t)prm.stride,
                        frame_bytes, &mbars[team]);
       // nothing after the last barrier reads the exchange buffers, so the next group may start at once;
       // segsum/featbuf are rewritten only after the next group's barriers.

@@ -110,7 +110,7 @@ void CE_Predictive_Node::execute() {
   // handle samples (.cpp:146-154): stage the packet in the pinned ring and commit it
   if (ECR->CE_metrics.CE_event == ExtensibleCognitiveRadio::USRP_RX_SAMPS) {
     fft_counter++;
-    float *slot = NULL;
+    void *slot = NULL;
     int st = crn_ring_acquire(sense, &slot);
     if (st == CRN_OK) {
       memcpy(slot, ECR->ce_usrp_rx_buffer, (size_t)ECR->ce_usrp_rx_buffer_length * sizeof(float) * 2);

@@ -53,6 +53,11 @@ enum crn_window { CRN_WINDOW_RECT = 0, CRN_WINDOW_HANN = 1 };
 enum crn_detector { CRN_DET_MAG = 0, CRN_DET_MAGSQ = 1 };
 enum crn_postop { CRN_POST_SQUARE_OF_SUM = 0, CRN_POST_SUM = 1 };
 enum crn_decide { CRN_DECIDE_NONE = 0, CRN_DECIDE_ANN = 1, CRN_DECIDE_ENERGY = 2 };
+/* Sample format of every IQ buffer handed to the library.  CF32: interleaved float32 (re,im), 8 B/sample -
+   what UHD's fc32 host format and ce_usrp_rx_buffer hold.  SC16: interleaved int16 (I,Q), 4 B/sample - the
+   USRP's over-the-wire format (UHD otw_format "sc16"); sample value = int16 / 32768.  Converting on the GPU
+   halves the bytes that cross PCIe on the live-ingest path. */
+enum crn_iq_format { CRN_IQ_CF32 = 0, CRN_IQ_SC16 = 1 };
 
 /* Outcome of the reference's first-match chain, CE_Predictive_Node.cpp:245-261. */
 enum crn_decision {
@@ -96,6 +101,8 @@ typedef struct crn_config {
   double energy_factor;  /* CRN_DECIDE_ENERGY: band c is occupied iff feat[c] > energy_factor * min_c feat */
   int32_t device;        /* CUDA device ordinal */
   int32_t ring_slots;    /* streaming API: number of K-frame decision slots in the pinned ring (>= 2) */
+  int32_t iq_format;     /* enum crn_iq_format of all IQ buffers (ring slots, batch host/device)            */
+  int32_t reserved_;     /* keep the struct a multiple of 8 bytes */
 } crn_config;
 
 /* One decision (K frames).  Replaces the locals/members the reference only printf()s
@@ -139,10 +146,10 @@ int crn_destroy(crn_handle *h);
 
 /* ---- streaming path: what a CognitiveEngine::execute() calls per USRP_RX_SAMPS event ---------- */
 
-/* Pointer to the pinned host slot for the NEXT frame (frame_len samples, 8*L bytes).  This is the
+/* Pointer to the pinned host slot for the NEXT frame (frame_len samples; 8*L bytes CF32, 4*L bytes SC16).  This is the
    memcpy target that replaces ECR->ce_usrp_rx_buffer in the rx-worker handoff
    (src/extensible_cognitive_radio.cpp:1316-1317) / the engine's own memcpy (.cpp:149). */
-int crn_ring_acquire(crn_handle *h, float **slot);
+int crn_ring_acquire(crn_handle *h, void **slot);
 
 /* Commit `nframes` (normally 1) frames written through crn_ring_acquire.  Non-blocking and stream
    ordered.  When the K-th frame of a decision has been committed the K frames are copied to the GPU
@@ -159,10 +166,10 @@ int crn_reset(crn_handle *h);
 
 /* ---- batch path ------------------------------------------------------------------------------- */
 
-/* ngroups decisions from HOST memory: iq holds ngroups*K frames (frame f at iq + 2*f*frame_stride
-   floats).  Stages through pinned buffers, host->device copy, kernel, device->host read of the
+/* ngroups decisions from HOST memory: iq holds ngroups*K frames in cfg.iq_format (frame f starts at sample
+   f*frame_stride).  Stages through pinned buffers, host->device copy, kernel, device->host read of the
    results; returns when results[0..ngroups) are filled. */
-int crn_sense_batch_host(crn_handle *h, const float *iq, int64_t ngroups, crn_result *results);
+int crn_sense_batch_host(crn_handle *h, const void *iq, int64_t ngroups, crn_result *results);
 
 /* ngroups decisions from DEVICE memory, asynchronous on `cuda_stream` (a cudaStream_t; NULL = the
    legacy default stream).  Output arrays are device pointers; any of d_ann / d_decision / d_mask may

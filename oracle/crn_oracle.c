@@ -44,12 +44,16 @@ static void sense_group(const crn_config *c, const float *iq, fftplan plan, cf32
   const int N = c->nfft, L = c->frame_len, K = c->navg;
   const int stride = c->frame_stride > 0 ? c->frame_stride : L;
   memset(avg, 0, sizeof(float) * N); /* .cpp:39,287 */
+  const int sc16 = (c->iq_format == CRN_IQ_SC16);
   for (int k = 0; k < K; k++) {
     const float *fr = iq + 2 * (size_t)k * stride;
+    const int16_t *fr16 = (const int16_t *)iq + 2 * (size_t)k * stride;
     /* .cpp:149: memcpy of L samples into buffer[N]; the tail stays zero */
     for (int n = 0; n < N; n++) {
       if (n < L) {
-        float re = fr[2 * n], im = fr[2 * n + 1];
+        /* sc16 wire samples are what UHD converts to fc32 before the engine sees them: value = int16/32768 */
+        float re = sc16 ? (float)fr16[2 * n] * (1.0f / 32768.0f) : fr[2 * n];
+        float im = sc16 ? (float)fr16[2 * n + 1] * (1.0f / 32768.0f) : fr[2 * n + 1];
         if (win) { re *= win[n]; im *= win[n]; }
         buf[n] = re + im * _Complex_I;
       } else {
@@ -126,7 +130,7 @@ static void *sense_worker(void *arg) {
   const crn_config *c = j->c;
   const int N = c->nfft;
   const int stride = c->frame_stride > 0 ? c->frame_stride : c->frame_len;
-  const size_t group_floats = 2 * (size_t)stride * c->navg;
+  const size_t group_floats = (c->iq_format == CRN_IQ_SC16 ? 1 : 2) * (size_t)stride * c->navg; /* 4-byte units */
   cf32 *buf = (cf32 *)calloc(N, sizeof(cf32));
   cf32 *spec = (cf32 *)calloc(N, sizeof(cf32));
   float *avg = (float *)calloc(N, sizeof(float));

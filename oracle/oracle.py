@@ -78,12 +78,17 @@ def _iq_f32(iq):
 
 def sense_port(cfg, iq, ngroups=None, nthreads=1):
     """cfg: crn_b200.Config (same struct the GPU library takes).  Returns (feat, ann, decision, mask)."""
-    iq = _iq_f32(iq)
     stride = cfg.frame_stride if cfg.frame_stride > 0 else cfg.frame_len
     gs = stride * cfg.navg
+    if getattr(cfg, "iq_format", 0) == 1:      # sc16: interleaved int16 (I,Q)
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+        nsamp = iq.size // 2
+    else:
+        iq = _iq_f32(iq)
+        nsamp = iq.size
     if ngroups is None:
-        ngroups = iq.size // gs
-    assert ngroups * gs <= iq.size
+        ngroups = nsamp // gs
+    assert ngroups * gs <= nsamp
     feat = np.zeros((ngroups, cfg.nbands), np.float32)
     ann = np.zeros((ngroups, 3), np.float64)
     dec = np.zeros(ngroups, np.int32)
@@ -95,7 +100,7 @@ def sense_port(cfg, iq, ngroups=None, nthreads=1):
 
 
 def time_port(cfg, iq, ngroups, nthreads):
-    iq = _iq_f32(iq)
+    iq = np.ascontiguousarray(iq, dtype=np.int16) if getattr(cfg, "iq_format", 0) == 1 else _iq_f32(iq)
     return port().crn_oracle_time(C.byref(cfg), iq.ctypes.data, ngroups, nthreads)
 
 

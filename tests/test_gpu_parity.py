@@ -402,3 +402,105 @@ def test_full_size_parseval_and_sampled_parity(crn, oracle, torch):
         rhs[g0:g0 + blk.shape[0]] = ((blk ** 2).sum(dim=3) * win ** 2).sum(dim=(1, 2)) * (nfft / K)
     rel = ((lhs - rhs).abs() / rhs).max().item()
     assert rel <= 2e-5, rel
+
+
+@pytest.mark.parametrize("nfft,mode,navg", [(512, "ref", 10), (1024, "welch", 64), (8192, "wide", 4), (2048, "welch", 7)])
+def test_sc16_wire_format(crn, oracle, torch, nfft, mode, navg):
+    """SC16 ingest: int16 (I,Q) pairs converted on the GPU; same results as the oracle fed the
+    same int16 samples (value = int16/32768), through the device, host-batch and streaming paths."""
+    cfg = make_cfg(crn, nfft, navg, mode, nfft, 0)
+    cfg.iq_format = crn.IQ_SC16
+    gs = cfg.group_samples
+    ng = 5
+    sc = crn.synth_config(gs, dwell_groups=1, snr_db=10.0, seed=nfft)
+    iq, _ = oracle.synth(sc, ng * gs)
+    i16 = np.clip(np.round(iq.view(np.float32) * 32768.0), -32768, 32767).astype(np.int16)   # interleaved I,Q
+    want = oracle.sense_port(cfg, i16)
+    # the float path on the dequantised samples is the same thing by another route
+    fcfg = make_cfg(crn, nfft, navg, mode, nfft, 0)
+    want_f = oracle.sense_port(fcfg, (i16.astype(np.float32) / 32768.0).view(np.complex64))
+    assert feat_close(want[0], want_f[0], 1e-6)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_iq = torch.from_numpy(i16).cuda()
+    d_feat = torch.empty(ng, cfg.nbands, dtype=torch.float32, device="cuda")
+    d_ann = torch.empty(ng, 3, dtype=torch.float64, device="cuda")
+    d_dec = torch.empty(ng, dtype=torch.int32, device="cuda")
+    d_mask = torch.empty(ng, dtype=torch.int64, device="cuda")
+    with crn.Sensor(cfg, device=0) as s:
+        assert s.kernel_info()["name"].endswith("_sc16")
+        s.sense_device(d_iq, ng, d_feat, d_ann, d_dec, d_mask, stream)
+        torch.cuda.synchronize()
+        got = (d_feat.cpu().numpy(), d_ann.cpu().numpy(), d_dec.cpu().numpy(), d_mask.cpu().numpy().view(np.uint64))
+        check(crn, cfg, got, want)
+        host = s.sense_host(i16)
+        for a, b in zip(got, host):
+            assert np.array_equal(a, b)
+        if nfft == 512:   # streaming ring with 4-byte samples
+            out = []
+            for fr in i16.reshape(-1, 2 * cfg.frame_len):
+                s.push_frame(fr)
+                r = s.poll()
+                if r is not None:
+                    out.append(r)
+            while len(out) < ng:
+                out.append(s.wait())
+            assert np.array_equal(np.array([r.decision for r in out]), got[2])
+            assert np.array_equal(np.array([[r.feat[b] for b in range(4)] for r in out], np.float32), got[0])
+
+
+def test_error_paths_return_codes_not_exits(crn, torch):
+    """Every misuse comes back as a status + message (the reference printf()s and exit()s instead)."""
+    cfg = crn.config_reference()
+    with crn.Sensor(cfg, device=0) as s:
+        lib = crn.lib
+        assert lib.crn_submit(s._h, 0) == crn.ERR_INVALID
+        assert lib.crn_submit(s._h, 11) == crn.ERR_INVALID          # would cross a decision boundary
+        assert lib.crn_poll(s._h, None) == crn.ERR_INVALID
+        r = crn.Result()
+        assert lib.crn_poll(s._h, C.byref(r)) == crn.ERR_NOT_READY
+        assert lib.crn_wait(s._h, C.byref(r)) == crn.ERR_NOT_READY  # nothing in flight: no deadlock
+        assert lib.crn_sense_batch_device(s._h, None, 1, None, None, None, None, None) == crn.ERR_INVALID
+        assert lib.crn_sense_batch_host(s._h, None, 1, None) == crn.ERR_INVALID
+        assert lib.crn_last_error()
+        # a partially filled decision can be dropped (the reference zeroes fft_avg/fft_counter, .cpp:287-288)
+        fr = np.ones(512, np.complex64)
+        for _ in range(4):
+            s.push_frame(fr)
+        s.reset()
+        for _ in range(10):
+            s.push_frame(np.zeros(512, np.complex64))
+        out = s.wait()
+        assert out.decision == crn.ALL_BUSY and out.feat[1] == 0.0   # the four dropped frames left no trace
+    bad = crn.config_reference()
+    bad.device = 99
+    with pytest.raises(crn.CrnError) as ei:
+        crn.Sensor(bad)
+    assert ei.value.status == crn.ERR_NO_DEVICE
+    assert crn.lib.crn_destroy(None) == crn.OK
+
+
+def test_two_threads_two_handles(crn, oracle, torch):
+    """One handle per radio/thread (the reference's threading contract); handles do not interfere."""
+    import threading
+    g = np.load(os.path.join(GOLDEN, "ref_markov_L512.npz"))
+    frames = g["iq"].reshape(-1, 512)
+    results = {}
+
+    def radio(name):
+        cfg = crn.config_reference()
+        out = []
+        with crn.Sensor(cfg, device=0) as s:
+            for rep in range(3):
+                for i, fr in enumerate(frames):
+                    s.push_frame(fr)
+                    if (i + 1) % 10 == 0:
+                        out.append(s.wait().decision)
+        results[name] = out
+
+    th = [threading.Thread(target=radio, args=(n,)) for n in ("a", "b", "c")]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    want = g["decision"].tolist() * 3
+    assert results["a"] == want and results["b"] == want and results["c"] == want
