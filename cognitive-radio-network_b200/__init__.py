@@ -24,7 +24,8 @@ OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_OVERRUN, ERR_NOT_READY, ERR_UNSUPPORTED = range(-1, -8, -1)
 WINDOW_RECT, WINDOW_HANN = 0, 1
 DET_MAG, DET_MAGSQ = 0, 1
-POST_SQUARE_OF_SUM, POST_SUM = 0, 1
+POST_SQUARE_OF_SUM, POST_SUM, POST_SUM_DB = 0, 1, 2
+FUSE_OR, FUSE_MAJORITY, FUSE_AND = 0, 1, 2
 DECIDE_NONE, DECIDE_ANN, DECIDE_ENERGY = 0, 1, 2
 ALL_BUSY, CH1_OCCUPIED, CH2_OCCUPIED, CH3_OCCUPIED = 0, 1, 2, 3
 IQ_CF32, IQ_SC16 = 0, 1
@@ -107,6 +108,7 @@ API = {
     "crn_synth_config_default": (C.c_int, [C.POINTER(SynthConfig), C.c_int32]),
     "crn_synth_generate_device": (C.c_int, [C.POINTER(SynthConfig), C.c_int32, _P, C.c_int64, C.c_int64, _P, _P]),
     "crn_synth_generate_streams_device": (C.c_int, [C.POINTER(SynthConfig), C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
+    "crn_fuse_masks_device": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "crn_strerror": (C.c_char_p, [C.c_int]),
     "crn_last_error": (C.c_char_p, []),
     "crn_version": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -322,6 +324,12 @@ def synth_generate_streams(sc, d_iq, first_stream, nstreams, samples_per_stream,
     _check(lib.crn_synth_generate_streams_device(C.byref(sc), device, _ptr(d_iq), first_stream, nstreams,
                                                  samples_per_stream, _ptr(d_state), C.c_void_p(stream)),
            "crn_synth_generate_streams_device")
+
+
+def fuse_masks(d_masks, nradios, nslots, nbands, mode, d_fused, device=0, stream=0):
+    """Cooperative hard-decision fusion of occupancy masks [nradios][nslots] -> [nslots] on the GPU."""
+    _check(lib.crn_fuse_masks_device(_ptr(d_masks), nradios, nslots, nbands, mode, _ptr(d_fused), device,
+                                     C.c_void_p(stream)), "crn_fuse_masks_device")
 
 
 def shard_groups(ngroups, world_size, rank):

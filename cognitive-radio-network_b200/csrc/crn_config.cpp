@@ -138,7 +138,7 @@ int crn_config_validate(const crn_config *c) {
     return crn::fail(CRN_ERR_INVALID, "unknown window");
   if (c->detector != CRN_DET_MAG && c->detector != CRN_DET_MAGSQ)
     return crn::fail(CRN_ERR_INVALID, "unknown detector");
-  if (c->postop != CRN_POST_SQUARE_OF_SUM && c->postop != CRN_POST_SUM)
+  if (c->postop != CRN_POST_SQUARE_OF_SUM && c->postop != CRN_POST_SUM && c->postop != CRN_POST_SUM_DB)
     return crn::fail(CRN_ERR_INVALID, "unknown postop");
   if (c->decide < CRN_DECIDE_NONE || c->decide > CRN_DECIDE_ENERGY)
     return crn::fail(CRN_ERR_INVALID, "unknown decide mode");

@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
           m *= prm.invK;
           const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
           featbuf[b] = f;
-          prm.feat[(size_t)g * prm.nbands + b] = f;
+          prm.feat[(size_t)g * prm.nbands + b] = (prm.postop == CRN_POST_SUM_DB) ? 10.0f * log10f(f) : f;
         }
         __syncwarp();
         decide_and_store(prm, featbuf, g, tid);
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
           m *= prm.invK;
           const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
           fb[b] = f;
-          prm.feat[(size_t)g * prm.nbands + b] = f;
+          prm.feat[(size_t)g * prm.nbands + b] = (prm.postop == CRN_POST_SUM_DB) ? 10.0f * log10f(f) : f;
         }
         __syncwarp();
         if (lane == 0) {

@@ -51,7 +51,9 @@ enum {
 
 enum crn_window { CRN_WINDOW_RECT = 0, CRN_WINDOW_HANN = 1 };
 enum crn_detector { CRN_DET_MAG = 0, CRN_DET_MAGSQ = 1 };
-enum crn_postop { CRN_POST_SQUARE_OF_SUM = 0, CRN_POST_SUM = 1 };
+/* SUM_DB: the reported feature is 10 log10(sum) in dB (Welch band power in dB); the MLP / energy detector
+   still see the linear sum. */
+enum crn_postop { CRN_POST_SQUARE_OF_SUM = 0, CRN_POST_SUM = 1, CRN_POST_SUM_DB = 2 };
 enum crn_decide { CRN_DECIDE_NONE = 0, CRN_DECIDE_ANN = 1, CRN_DECIDE_ENERGY = 2 };
 /* Sample format of every IQ buffer handed to the library.  CF32: interleaved float32 (re,im), 8 B/sample -
    what UHD's fc32 host format and ce_usrp_rx_buffer hold.  SC16: interleaved int16 (I,Q), 4 B/sample - the
@@ -177,6 +179,17 @@ int crn_sense_batch_host(crn_handle *h, const void *iq, int64_t ngroups, crn_res
    d_mask: uint64[ngroups].  IQ is read from HBM exactly once; only these features are written. */
 int crn_sense_batch_device(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat,
                            double *d_ann, int32_t *d_decision, uint64_t *d_mask, void *cuda_stream);
+
+/* ---- cooperative sensing -------------------------------------------------------------- */
+
+enum crn_fusion { CRN_FUSE_OR = 0, CRN_FUSE_MAJORITY = 1, CRN_FUSE_AND = 2 };
+
+/* Hard-decision fusion across cooperating radios (the CSS scheme of the reference's project documentation):
+   d_masks is uint64[nradios][nslots] (the occupancy_mask of radio r in time slot s, e.g. gathered from
+   several GPUs); d_fused[s] gets bit c set when band c is reported occupied by any / more than half / all
+   of the radios.  Asynchronous on cuda_stream. */
+int crn_fuse_masks_device(const uint64_t *d_masks, int64_t nradios, int64_t nslots, int32_t nbands,
+                          int32_t mode, uint64_t *d_fused, int32_t device, void *cuda_stream);
 
 /* ---- synthetic primary-user IQ (stands in for the USRP) ----------------------- */
 

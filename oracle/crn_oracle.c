@@ -77,15 +77,18 @@ static void sense_group(const crn_config *c, const float *iq, fftplan plan, cf32
   for (int b = 0; b < c->nbands; b++) m[b] = 0.0f;
   for (int s = 0; s < c->nsegs; s++)
     for (int i = c->segs[s].lo; i < c->segs[s].hi; i++) m[c->segs[s].band] += avg[i];
-  for (int b = 0; b < c->nbands; b++)
-    feat[b] = (c->postop == CRN_POST_SQUARE_OF_SUM) ? m[b] * m[b] : m[b];
+  float lin[CRN_MAX_BANDS]; /* linear features: what the MLP / energy detector see */
+  for (int b = 0; b < c->nbands; b++) {
+    lin[b] = (c->postop == CRN_POST_SQUARE_OF_SUM) ? m[b] * m[b] : m[b];
+    feat[b] = (c->postop == CRN_POST_SUM_DB) ? 10.0f * log10f(lin[b]) : lin[b];
+  }
 
   double out[CRN_ANN_OUTPUTS + 1] = {0, 0, 0, 0};
   int dec = 0;
   uint64_t msk = 0;
   if (c->decide == CRN_DECIDE_ANN) {
     /* .cpp:200: Features_Buffer = {0, NF^2, CH1, CH2, CH3} == features 0..3 */
-    double F[CRN_ANN_INPUTS + 1] = {0, feat[0], feat[1], feat[2], feat[3]};
+    double F[CRN_ANN_INPUTS + 1] = {0, lin[0], lin[1], lin[2], lin[3]};
     double H[CRN_ANN_HIDDEN + 1];
     for (int j = 1; j <= CRN_ANN_HIDDEN; j++) { /* .cpp:214-220 */
       double sum = c->ann_wih[0][j];
@@ -104,10 +107,10 @@ static void sense_group(const crn_config *c, const float *iq, fftplan plan, cf32
     else dec = CRN_ALL_BUSY;
     msk = dec ? (1ull << (dec - 1)) : 0;
   } else if (c->decide == CRN_DECIDE_ENERGY) {
-    float mn = feat[0];
-    for (int b = 1; b < c->nbands; b++) mn = feat[b] < mn ? feat[b] : mn;
+    float mn = lin[0];
+    for (int b = 1; b < c->nbands; b++) mn = lin[b] < mn ? lin[b] : mn;
     for (int b = 0; b < c->nbands; b++)
-      if ((double)feat[b] > c->energy_factor * (double)mn) msk |= (1ull << b);
+      if ((double)lin[b] > c->energy_factor * (double)mn) msk |= (1ull << b);
   }
   if (ann) { ann[0] = out[1]; ann[1] = out[2]; ann[2] = out[3]; }
   if (decision) *decision = dec;

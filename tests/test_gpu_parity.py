@@ -504,3 +504,36 @@ def test_two_threads_two_handles(crn, oracle, torch):
         t.join()
     want = g["decision"].tolist() * 3
     assert results["a"] == want and results["b"] == want and results["c"] == want
+
+
+def test_db_features(crn, oracle, torch):
+    """Welch band power in dB: within 1e-3 dB of the oracle (north_star tolerance); the MLP still sees the
+    linear powers, so decisions equal the linear-mode run."""
+    cfg = crn.config_welch(1024, 16)
+    lin = run_device(crn, torch, cfg, *[oracle.synth(crn.synth_config(cfg.group_samples, dwell_groups=1, seed=4), 6 * cfg.group_samples)[0]])
+    cfg.postop = crn.POST_SUM_DB
+    iq, _ = oracle.synth(crn.synth_config(cfg.group_samples, dwell_groups=1, seed=4), 6 * cfg.group_samples)
+    got = run_device(crn, torch, cfg, iq)
+    want = oracle.sense_port(cfg, iq)
+    assert np.abs(got[0] - want[0]).max() <= 1e-3                       # dB
+    assert np.abs(got[0] - 10 * np.log10(lin[0])).max() <= 1e-3
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[2], lin[2])
+    assert np.abs(got[1] - want[1]).max() <= ANN_ATOL
+
+
+def test_cooperative_fusion(crn, torch):
+    rng = np.random.default_rng(5)
+    nradios, nslots, nbands = 7, 1000, 64
+    masks = rng.integers(0, 2 ** 63, size=(nradios, nslots), dtype=np.uint64) & rng.integers(0, 2 ** 63, size=(nradios, nslots), dtype=np.uint64)
+    d_masks = torch.from_numpy(masks.view(np.int64)).cuda()
+    d_out = torch.empty(nslots, dtype=torch.int64, device="cuda")
+    bits = ((masks[:, :, None] >> np.arange(nbands, dtype=np.uint64)) & np.uint64(1)).astype(np.int64)
+    weights = (np.uint64(1) << np.arange(nbands, dtype=np.uint64))
+    for mode, ref_bits in ((crn.FUSE_OR, bits.any(axis=0)), (crn.FUSE_MAJORITY, 2 * bits.sum(axis=0) > nradios),
+                           (crn.FUSE_AND, bits.all(axis=0))):
+        crn.fuse_masks(d_masks, nradios, nslots, nbands, mode, d_out, 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want = (ref_bits.astype(np.uint64) * weights).sum(axis=1, dtype=np.uint64)
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint64), want)
+    with pytest.raises(crn.CrnError):
+        crn.fuse_masks(d_masks, 0, nslots, nbands, 0, d_out)
