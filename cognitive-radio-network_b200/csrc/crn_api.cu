@@ -52,6 +52,7 @@ struct crn_handle {
   int num_sms = 0;
   int stride = 0;
   size_t sample_bytes = 8;  // 8 (CF32) or 4 (SC16)
+  bool allow_tma = true;    // CRN_NO_TMA=1 (read once at create) forces plain loads: A/B measurements
   crn::sense_launch_fn launch = nullptr;
   crn::LaunchGeometry geo;
   crn::SenseParams base;  // everything but iq / outputs / ngroups
@@ -193,8 +194,7 @@ int launch(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat, doub
   p.mask = d_mask;
   p.ngroups = ngroups;
   // bulk-copy (TMA) staging needs 16-byte aligned frame addresses and sizes; anything else uses plain loads
-  const char *no_tma = getenv("CRN_NO_TMA");
-  p.use_tma = (p.upg == 0) && !(no_tma && no_tma[0] == '1') && ((reinterpret_cast<uintptr_t>(d_iq) & 15) == 0) &&
+  p.use_tma = (p.upg == 0) && h->allow_tma && ((reinterpret_cast<uintptr_t>(d_iq) & 15) == 0) &&
               ((h->stride * h->sample_bytes) % 16 == 0) && ((h->cfg.frame_len * h->sample_bytes) % 16 == 0);
   int st = h->launch(p, h->cfg.window, h->cfg.detector, grid_for(h, ngroups), s, nullptr);
   if (st == CRN_OK) h->launches++;
@@ -307,6 +307,8 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   {
     const int teams = h->geo.teams;
     const bool long_even_groups = (cfg->navg % teams == 0) && (cfg->navg / teams >= 8);
+    const char *no_tma = getenv("CRN_NO_TMA");
+    h->allow_tma = !(no_tma && no_tma[0] == '1');
     const char *force = getenv("CRN_EPI");  // "cta" | "unit": development override
     bool cta = long_even_groups;
     if (force && !strcmp(force, "cta")) cta = true;

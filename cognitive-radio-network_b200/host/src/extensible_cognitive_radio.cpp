@@ -9,22 +9,12 @@
 #include <string.h>
 #include <sys/time.h>
 
-#include <map>
 
 void *ECR_rx_worker(void *arg);
 void *ECR_ce_worker(void *arg);
 
-namespace {
-std::map<std::string, crn_ce_factory> &registry() {
-  static std::map<std::string, crn_ce_factory> r;
-  return r;
-}
-}  // namespace
-
-bool crn_register_ce(const char *name, crn_ce_factory f) {
-  registry()[name] = f;
-  return true;
-}
+// engine registry: src/plugin.cpp
+CognitiveEngine *crn_create_ce(const char *name, int argc, char **argv, ExtensibleCognitiveRadio *ecr);
 
 // ---- file source ------------------------------------------------------------------------------------
 FileIqSource::FileIqSource(const std::string &path, bool loop) : fp_(fopen(path.c_str(), "rb")), loop_(loop) {}
@@ -83,13 +73,12 @@ ExtensibleCognitiveRadio::~ExtensibleCognitiveRadio() {
 }
 
 void ExtensibleCognitiveRadio::set_ce(char *ce, int argc, char **argv) {
-  std::map<std::string, crn_ce_factory>::iterator it = registry().find(ce);
-  if (it == registry().end()) {
+  CE = crn_create_ce(ce, argc, argv, this);
+  if (!CE) {
     // same convention as upstream (src/crts.cpp:306-310): an unknown engine is fatal
     printf("The cognitive engine %s is not registered with this radio.\n", ce);
     exit(EXIT_FAILURE);
   }
-  CE = it->second(argc, argv, this);
 }
 
 void ExtensibleCognitiveRadio::start_ce() {
