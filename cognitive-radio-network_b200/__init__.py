@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrnsense.so")
+LIB_PATH = os.environ.get("CRN_LIB") or os.path.join(_HERE, "libcrnsense.so")  # CRN_LIB: A/B build variants
 
 MAX_BANDS = 64
 MAX_SEGS = 128

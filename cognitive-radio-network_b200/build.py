@@ -43,9 +43,9 @@ def _digest():
     return h.hexdigest()
 
 
-def _compile(nvcc, src, verbose):
-    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
-    cmd = [nvcc] + ARCH + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+def _compile(nvcc, src, verbose, objdir=OBJ, defs=()):
+    obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+    cmd = [nvcc] + ARCH + NVCC_FLAGS + list(defs) + (["-Xptxas", "-v"] if verbose else []) + \
           ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -81,5 +81,29 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defs, verbose=False):
+    """Development aid: the same library compiled with extra -D switches into variants/libcrnsense_<name>.so
+    (A/B timing of one kernel decision on the GPU box; select it with CRN_LIB=<path> at import)."""
+    vdir = os.path.join(HERE, "variants")
+    objdir = os.path.join(vdir, "build_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    lib = os.path.join(vdir, "libcrnsense_%s.so" % name)
+    nvcc = _nvcc()
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        res = list(ex.map(lambda s: _compile(nvcc, s, verbose, objdir, defs), SOURCES))
+    r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", lib] + sorted(o for o, _ in res) +
+                       ["-lcudart_static", "-lpthread", "-ldl", "-lrt"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if verbose:
+        for s, (_, log) in zip(SOURCES, res):
+            sys.stderr.write("== %s\n%s" % (s, log))
+    return lib
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:  # python build.py --variant NAME -DFOO -DBAR=1
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")], "-v" in sys.argv))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

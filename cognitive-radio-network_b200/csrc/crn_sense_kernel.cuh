@@ -236,8 +236,8 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
         const float2 w = winp[m0 * T + t];
         butterfly_w_real(a[m0], a[m0 + E / 2], w.x, w.y, v[br], v[br + 1]);
       } else {
-        v[br] = make_float2(a[m0].x + a[m0 + E / 2].x, a[m0].y + a[m0 + E / 2].y);
-        v[br + 1] = make_float2(a[m0].x - a[m0 + E / 2].x, a[m0].y - a[m0 + E / 2].y);
+        v[br] = add2(a[m0], a[m0 + E / 2]);
+        v[br + 1] = sub2(a[m0], a[m0 + E / 2]);
       }
     });
     fft_dit<R, 2>(v);
