@@ -296,6 +296,14 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     b.seg_lo[s] = (short)cfg->segs[s].lo;
     b.seg_hi[s] = (short)cfg->segs[s].hi;
   }
+  {  // spectrum slices (accumulator registers) the band table reads: selects the pruned kernel when it can
+    const crn::RadixPlan rp = crn::radix_plan(cfg->nfft);
+    const int per_slice = cfg->nfft / rp.e;
+    const char *full = getenv("CRN_NO_PRUNE");  // development override: always the all-bins kernel
+    b.acc_mask = (full && full[0] == '1') ? 0xFFFFFFFFu : 0u;
+    for (int s = 0; s < cfg->nsegs; s++)
+      for (int k = cfg->segs[s].lo; k < cfg->segs[s].hi; k++) b.acc_mask |= 1u << (k / per_slice);
+  }
 
   st = h->launch(b, cfg->window, cfg->detector, 0, nullptr, &h->geo);
   if (st != CRN_OK) return st;

@@ -22,9 +22,9 @@ struct LaunchGeometry {
 typedef int (*sense_launch_fn)(const SenseParams &prm, int window, int detector, int grid,
                                cudaStream_t stream, LaunchGeometry *geo_only);
 
-template <class P, bool WIN, int DET, int EPI, bool SC16>
-int launch_fmt(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
-  auto kern = sense_kernel<P, WIN, DET, EPI, SC16>;
+template <class P, bool WIN, int DET, int EPI, bool SC16, unsigned AMASK>
+int launch_msk(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
+  auto kern = sense_kernel<P, WIN, DET, EPI, SC16, AMASK>;
   const size_t smem = P::smem_bytes(WIN);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
@@ -44,15 +44,23 @@ int launch_fmt(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeom
     geo->teams = P::TEAMS;
     geo->units = P::UNITS;
     geo->teams_per_unit = P::TEAMS_PER_UNIT;
-    snprintf(geo->name, sizeof(geo->name), "sense_n%d_r%dx%dx%d_%s_%s_%s%s", P::N, P::R0, P::R1, P::R2,
+    snprintf(geo->name, sizeof(geo->name), "sense_n%d_r%dx%dx%d_%s_%s_%s%s%s", P::N, P::R0, P::R1, P::R2,
              WIN ? "hann" : "rect", DET == DET_MAGSQ ? "magsq" : "mag", EPI == EPI_CTA ? "cta" : "unit",
-             SC16 ? "_sc16" : "");
+             SC16 ? "_sc16" : "", AMASK == full_acc_mask<P::E>() ? "" : "_refbins");
     return CRN_OK;
   }
   kern<<<grid, P::NT, smem, stream>>>(prm);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "sense kernel launch: %s", cudaGetErrorString(e));
   return CRN_OK;
+}
+
+// Band tables that stay inside the reference engine's bin plan run the kernel pruned to those spectrum slices.
+template <class P, bool WIN, int DET, int EPI, bool SC16>
+int launch_fmt(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
+  constexpr unsigned REF = ref_acc_mask<P::E>(), FULL = full_acc_mask<P::E>();
+  return (prm.acc_mask & ~REF) == 0 ? launch_msk<P, WIN, DET, EPI, SC16, REF>(prm, grid, stream, geo)
+                                    : launch_msk<P, WIN, DET, EPI, SC16, FULL>(prm, grid, stream, geo);
 }
 
 template <class P, bool WIN, int DET, int EPI>

@@ -55,6 +55,7 @@ struct SenseParams {
   int upg;               // reduction units per decision group (divides UNITS); 0 = CTA-wide epilogue
   int use_tma;           // 1: stage frames with cp.async.bulk (needs 16-byte aligned frames, CTA epilogue)
   int sc16;              // IQ buffers hold int16 pairs (4 B/sample) instead of float pairs
+  unsigned acc_mask;     // bit m set: some band segment reads a bin held in accumulator register m
   double threshold, energy_factor;
   double wih[CRN_ANN_INPUTS + 1][CRN_ANN_HIDDEN + 1];
   double who[CRN_ANN_HIDDEN + 1][CRN_ANN_OUTPUTS + 1];
@@ -84,7 +85,11 @@ struct Plan {
   // exchange is a multi-warp barrier (measured on the generic three-pass plans: +8 % at N = 4096, +13 % at
   // N = 8192); for the one-warp-per-frame sizes plain coalesced loads plus the L2 prefetch are faster and
   // leaner in registers (1024: 599 vs 608 GS/s in the same binary, and 684 without the staging code).
+#ifdef CRN_TMA_ALL
+  static constexpr bool TMA = true;
+#else
   static constexpr bool TMA = (T > 64);
+#endif
 #ifdef CRN_NO_PREFETCH
   static constexpr bool PREFETCH = false;
 #else
@@ -129,9 +134,9 @@ struct HybridPlan {
   static constexpr bool HYBRID = true;
   // Bulk-copy (TMA) staging of the team's next frame into its (by then idle) exchange regions: the copy
   // flies under the last pass and the accumulate, so the next frame's first pass starts from shared memory.
-  // Measured (same binary, CRN_NO_TMA toggled): +12 % at N = 8192, +1 % at 2048; at 4096 the extra
-  // registers cost more than the staging wins (433 vs 448 GS/s), so it is compiled in for N = 8192 only.
-  static constexpr bool TMA = (N >= 8192);
+  // Measured with the packed-FP32 codelets (same binary, CRN_NO_TMA toggled): +5 % at N = 2048, +12 % at 4096,
+  // +5 % at 8192 (Welch) / +14 % (64 sub-channels).
+  static constexpr bool TMA = true;
   // At N = 8192 the 32 KB window table is what keeps a second CTA off the SM; there it is read through the
   // read-only L1 path instead (the table is reused by every frame, L1 keeps it).
   static constexpr bool WIN_SMEM = (N < 8192);
@@ -376,6 +381,26 @@ __device__ __forceinline__ void decide_and_store(const SenseParams &prm, const f
   }
 }
 
+// Which accumulator registers a band plan needs.  After the last pass register m of a team thread holds a bin
+// of the m-th N/E-wide slice of the spectrum (Plan::bin_of), so a band table that covers only part of the
+// spectrum leaves whole registers unused - and with them the accumulate AND the butterflies of the last pass
+// that feed nothing else (the compiler prunes them once the outputs are dead).  The reference engine's plan
+// (CE_Predictive_Node.cpp:173-190: bins 0-15, 496-510, 55-84, 189-221, 300-309 of 512, scaled with N) touches
+// 10 of 32 slices; kernels are instantiated for that mask and for "all registers" (any other table).
+__host__ __device__ constexpr unsigned slices_of(int lo, int hi, int per_slice) {
+  unsigned m = 0;
+  for (int b = lo; b < hi; b++) m |= 1u << (b / per_slice);
+  return m;
+}
+template <int E>
+__host__ __device__ constexpr unsigned ref_acc_mask() {
+  constexpr int W = 512 / E;  // slice width at N = 512
+  return slices_of(0, 16, W) | slices_of(496, 511, W) | slices_of(55, 85, W) | slices_of(189, 222, W) |
+         slices_of(300, 310, W);
+}
+template <int E>
+__host__ __device__ constexpr unsigned full_acc_mask() { return E >= 32 ? 0xFFFFFFFFu : ((1u << E) - 1u); }
+
 // EPI selects how the teams of a CTA share decision groups:
 //   EPI_CTA  - the whole CTA works on one group (team q takes frames q, q+TEAMS, ...) and meets at three
 //              CTA barriers per group to reduce; cheapest per group, best when a group is long (K >> TEAMS).
@@ -383,7 +408,7 @@ __device__ __forceinline__ void decide_and_store(const SenseParams &prm, const f
 //              warp busy when groups are short (reference mode: K = 10) or K does not divide by TEAMS.
 enum { EPI_CTA = 0, EPI_UNIT = 1 };
 
-template <class P, bool WIN, int DET, int EPI, bool SC16>
+template <class P, bool WIN, int DET, int EPI, bool SC16, unsigned AMASK>
 __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams prm) {
   using sample_t = typename std::conditional<SC16, unsigned, float2>::type;  // one IQ sample in memory
   constexpr int SPL = 128 / (int)sizeof(sample_t);                           // samples per 128-byte line
@@ -521,17 +546,19 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       }
       }  // !HYBRID
       // register m now holds bin P::bin_of(t, m)  (.cpp:152-154)
-#pragma unroll
-      for (int m = 0; m < E; m++) {
-        if constexpr (DET == DET_MAGSQ) {
-          acc[m] = fmaf(a[m].x, a[m].x, acc[m]);
-          acc[m] = fmaf(a[m].y, a[m].y, acc[m]);
-        } else {
-          float s;
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(a[m].x, a[m].x, a[m].y * a[m].y)));
-          acc[m] += s;
+      static_for<0, E>([&](auto M) {
+        constexpr int m = M.value;
+        if constexpr ((AMASK >> m) & 1u) {
+          if constexpr (DET == DET_MAGSQ) {
+            acc[m] = fmaf(a[m].x, a[m].x, acc[m]);
+            acc[m] = fmaf(a[m].y, a[m].y, acc[m]);
+          } else {
+            float s;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(a[m].x, a[m].x, a[m].y * a[m].y)));
+            acc[m] += s;
+          }
         }
-      }
+      });
     }
 
     if constexpr (EPI == EPI_CTA) {
@@ -540,8 +567,9 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       __syncthreads();          // every team finished reading its exchange buffer
       {
         float *mypart = reinterpret_cast<float *>(xb);  // N floats per team, aliasing the exchange buffer
-#pragma unroll
-        for (int m = 0; m < E; m++) mypart[P::bin_of(t, m)] = acc[m];
+        static_for<0, E>([&](auto M) {
+          if constexpr ((AMASK >> M.value) & 1u) mypart[P::bin_of(t, M.value)] = acc[M.value];
+        });
       }
       __syncthreads();
       {
@@ -599,13 +627,15 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
     const int slot = it & 1;
     if constexpr (TPU == 2) {  // two half-warp teams hold the same bins: fold them first
       __syncwarp();
-#pragma unroll
-      for (int m = 0; m < E; m++) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 16);
+      static_for<0, E>([&](auto M) {
+        if constexpr ((AMASK >> M.value) & 1u) acc[M.value] += __shfl_xor_sync(0xffffffffu, acc[M.value], 16);
+      });
     }
     unit_sync<T, UT>(unit);  // every thread of the unit is done reading its exchange buffer
     if (ut < T) {
-#pragma unroll
-      for (int m = 0; m < E; m++) part[P::bin_of(t, m)] = acc[m];
+      static_for<0, E>([&](auto M) {
+        if constexpr ((AMASK >> M.value) & 1u) part[P::bin_of(t, M.value)] = acc[M.value];
+      });
     }
     unit_sync<T, UT>(unit);
     {
