@@ -118,17 +118,17 @@ void unpack_result(const ResultBuf &r, int64_t i, int nbands, uint64_t first_fra
 }
 
 // Inter-pass twiddle tables, computed in double.  Pass p (Ns = product of earlier radices, radix R)
-// multiplies input q of FFT column j by W(q, j) = exp(-j 2 pi q (j mod Ns) / (Ns R)).  The first
-// butterfly stage pairs inputs q0 and q0 + R/2, so the table stores them side by side:
-//   tw[q0*Ns + jq] = { W(q0, jq), W(q0 + R/2, jq) },  q0 < R/2, jq < Ns.
+// multiplies input q of FFT column j by W(q, j) = exp(-j 2 pi q (j mod Ns) / (Ns R)).  The kernel reads only
+// q < R/2 (the partner q + R/2 is W(q) times a thread constant), two twiddles per 16-byte load:
+//   tw[(q/2)*Ns + jq] = { W(q, jq), W(q + 1, jq) },  q even < R/2, jq < Ns.
 void build_twiddles(const crn::RadixPlan &rp, std::vector<float4> &tw) {
   tw.clear();
   auto add = [&](int ns, int r) {
     const double step = -2.0 * M_PI / ((double)ns * (double)r);
-    for (int q0 = 0; q0 < r / 2; q0++)
+    for (int q = 0; q < r / 2; q += 2)
       for (int jq = 0; jq < ns; jq++) {
-        const double a = step * (double)((long long)q0 * jq);
-        const double b = step * (double)((long long)(q0 + r / 2) * jq);
+        const double a = step * (double)((long long)q * jq);
+        const double b = step * (double)((long long)(q + 1) * jq);
         tw.push_back(make_float4((float)cos(a), (float)sin(a), (float)cos(b), (float)sin(b)));
       }
   };

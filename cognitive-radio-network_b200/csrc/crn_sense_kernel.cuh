@@ -71,8 +71,8 @@ struct Plan {
   static constexpr int PASSES = (R2 > 1) ? 3 : 2;
   static constexpr int PADSHIFT = ilog2(R0);       // two pad slots per R0 points: conflict-free, 16 B rows
   static constexpr int XSZ = N + 2 * (N >> PADSHIFT);  // float2 slots per team exchange buffer
-  static constexpr int TW1 = R0 * R1 / 2;          // pass-1 paired twiddle table entries (float4)
-  static constexpr int TW2 = (R2 > 1) ? N / 2 : 0; // pass-2 paired twiddle table entries (float4)
+  static constexpr int TW1 = R0 * R1 / 4;          // pass-1 twiddle table entries (float4 = two twiddles)
+  static constexpr int TW2 = (R2 > 1) ? N / 4 : 0; // pass-2 twiddle table entries (float4 = two twiddles)
   static constexpr int UNIT_THREADS = T > 32 ? T : 32;
   static constexpr int UNITS = NT / UNIT_THREADS;  // reduction units per CTA
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
@@ -126,7 +126,7 @@ struct HybridPlan {
   static constexpr int PADSHIFT = 5;
   static constexpr int RS = 32 * (32 + 2);         // float2 slots of one warp's region (padded 32x32 exchange)
   static constexpr int XSZ = C * RS;
-  static constexpr int TW1 = 512;                  // paired 32x32 twiddles of the 1024-point FFT (float4)
+  static constexpr int TW1 = 256;                  // 32x32 twiddles of the 1024-point FFT, first half (float4)
   static constexpr int TW2 = 512;                  // W_N^n, n < 1024, as 1024 float2 = 512 float4
   static constexpr int UNIT_THREADS = T;
   static constexpr int UNITS = TEAMS;
@@ -251,24 +251,45 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
 }
 
 // Pass p >= 1: inter-pass twiddles W_{Ns*R}^{q*(j mod Ns)}, j = t + T*i, folded into the first stage.
-// twp[q0*NS + (j mod NS)] = {W(q0), W(q0 + R/2)}.
+// The stage pairs inputs q and q + R/2, and W(q + R/2) = W(q) * W(R/2) with W(R/2) = exp(-j pi (j mod Ns)/Ns)
+// the same for every q: a thread constant (`half`, one per codelet, computed once per kernel).  So only the
+// first R/2 twiddles come from shared memory - twp[(q/2)*NS + (j mod NS)] = {W(q), W(q+1)}, q even < R/2 -
+// and the partner costs one packed complex multiply: half the table wavefronts for 2 instructions per pair.
 template <int E, int R, int T, int NS>
-__device__ __forceinline__ void reg_pass_tw(float2 (&a)[E], const float4 *__restrict__ twp, int t) {
+__device__ __forceinline__ void reg_pass_tw(float2 (&a)[E], const float4 *__restrict__ twp, int t,
+                                            const float2 (&half)[E / R]) {
   constexpr int G = E / R;
   constexpr int LOG = ilog2(R);
   static_for<0, G>([&](auto I) {
     const int jq = (t + T * I.value) & (NS - 1);
     float2 v[R];
-    static_for<0, R / 2>([&](auto Q) {
-      constexpr int m0 = I.value + Q.value * G;
-      constexpr int br = bitrev(Q.value, LOG);
-      const float4 w = twp[Q.value * NS + jq];
-      butterfly_w_cplx<Q.value == 0>(a[m0], a[m0 + E / 2], make_float2(w.x, w.y), make_float2(w.z, w.w),
-                                     v[br], v[br + 1]);
+    static_for<0, R / 4>([&](auto Q2) {
+      const float4 w = twp[Q2.value * NS + jq];
+      static_for<0, 2>([&](auto H) {
+        constexpr int q = 2 * Q2.value + H.value;
+        constexpr int m0 = I.value + q * G;
+        constexpr int br = bitrev(q, LOG);
+        const float2 wa = H.value ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
+        if constexpr (q == 0) {
+          butterfly_w_cplx<true>(a[m0], a[m0 + E / 2], wa, half[I.value], v[br], v[br + 1]);
+        } else {
+          butterfly_w_cplx<false>(a[m0], a[m0 + E / 2], wa, cmul(wa, half[I.value]), v[br], v[br + 1]);
+        }
+      });
     });
     fft_dit<R, 2>(v);
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
+}
+// half[i] = exp(-j pi ((t + T i) mod NS) / NS); the argument is dyadic, sincospif is exact at it.
+template <int E, int R, int T, int NS>
+__device__ __forceinline__ void half_turn_twiddles(float2 (&half)[E / R], int t) {
+#pragma unroll
+  for (int i = 0; i < E / R; i++) {
+    float sn, cs;
+    sincospif((float)((t + T * i) & (NS - 1)) * (1.0f / (float)NS), &sn, &cs);
+    half[i] = make_float2(cs, -sn);
+  }
 }
 
 // Exchange rows are padded by two points: rows stay 16-byte aligned for the 16-byte stores of pass 0 and
@@ -455,6 +476,14 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
   }
   __syncthreads();
 
+  // thread-constant half-turn twiddles of the later passes (see reg_pass_tw)
+  constexpr int HR1 = P::HYBRID ? 32 : P::R1, HNS1 = P::HYBRID ? 32 : P::R0, HT1 = P::HYBRID ? 32 : T;
+  float2 half1[E / HR1];
+  half_turn_twiddles<E, HR1, HT1, HNS1>(half1, P::HYBRID ? (t & 31) : t);
+  constexpr int HR2 = (!P::HYBRID && P::PASSES == 3) ? P::R2 : E;
+  float2 half2[E / HR2];
+  if constexpr (!P::HYBRID && P::PASSES == 3) half_turn_twiddles<E, HR2, T, P::R0 * P::R1>(half2, t);
+
   const int L = prm.L, K = prm.K;
   const bool full = (L == N);
   const long long gstep = (long long)gridDim.x * GL;
@@ -523,7 +552,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
           team_sync<T>(team);  // every warp of the team has gathered its points: the regions are idle
           if (t == 0) tma_load_frame(xb, x + fstep, frame_bytes, &mbars[team]);
         }
-        reg_pass_tw<E, 32, 32, 32>(a, tw1, lane);
+        reg_pass_tw<E, 32, 32, 32>(a, tw1, lane, half1);
       } else {
       // pass 0 (Ns = 1: no twiddles; window folded in)
       reg_pass_first<E, P::R0, T, WIN>(a, winp, t);
@@ -538,11 +567,11 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       };
       if constexpr (P::PASSES == 2) stage_next();
       // pass 1
-      reg_pass_tw<E, P::R1, T, P::R0>(a, tw1, t);
+      reg_pass_tw<E, P::R1, T, P::R0>(a, tw1, t, half1);
       if constexpr (P::PASSES == 3) {
         exchange<E, P::R1, T, P::R0, P::PADSHIFT>(a, xb, t, team);
         stage_next();
-        reg_pass_tw<E, P::R2, T, P::R0 * P::R1>(a, tw2, t);
+        reg_pass_tw<E, P::R2, T, P::R0 * P::R1>(a, tw2, t, half2);
       }
       }  // !HYBRID
       // register m now holds bin P::bin_of(t, m)  (.cpp:152-154)
