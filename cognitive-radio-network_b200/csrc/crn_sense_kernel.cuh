@@ -85,16 +85,11 @@ struct Plan {
   // exchange is a multi-warp barrier (measured on the generic three-pass plans: +8 % at N = 4096, +13 % at
   // N = 8192); for the one-warp-per-frame sizes plain coalesced loads plus the L2 prefetch are faster and
   // leaner in registers (1024: 599 vs 608 GS/s in the same binary, and 684 without the staging code).
-#ifdef CRN_TMA_ALL
-  static constexpr bool TMA = true;
-#else
   static constexpr bool TMA = (T > 64);
-#endif
-#ifdef CRN_NO_PREFETCH
-  static constexpr bool PREFETCH = false;
-#else
-  static constexpr bool PREFETCH = true;           // software L2 prefetch one frame ahead
-#endif
+  // Software L2 prefetch one frame ahead.  Since the butterflies went to packed FP32 the one-warp-per-frame
+  // kernels are no longer short of issue slots and hide the load latency themselves; the prefetch then only
+  // adds L2 requests (measured: N = 512/1024 1-2 % faster without, N = 256 2 % faster with).
+  static constexpr bool PREFETCH = (N < 512);
   static_assert(R0 * R1 * R2 == N, "radices must multiply to N");
   static_assert(E % R0 == 0 && E % R1 == 0 && E % R2 == 0, "E must be a multiple of every radix");
   static_assert(R0 >= 16, "first radix < 16 would bank-conflict the exchange");
@@ -137,14 +132,10 @@ struct HybridPlan {
   // Measured with the packed-FP32 codelets (same binary, CRN_NO_TMA toggled): +5 % at N = 2048, +12 % at 4096,
   // +5 % at 8192 (Welch) / +14 % (64 sub-channels).
   static constexpr bool TMA = true;
-  // At N = 8192 the 32 KB window table is what keeps a second CTA off the SM; there it is read through the
-  // read-only L1 path instead (the table is reused by every frame, L1 keeps it).
-  static constexpr bool WIN_SMEM = (N < 8192);
-#ifdef CRN_NO_PREFETCH
-  static constexpr bool PREFETCH = false;
-#else
-  static constexpr bool PREFETCH = true;
-#endif
+  // From N = 4096 the window table (16 / 32 KB) is what keeps one more CTA off the SM; there it is read
+  // through the read-only L1 path instead (the table is reused by every frame, L1 keeps it).
+  static constexpr bool WIN_SMEM = (N < 4096);
+  static constexpr bool PREFETCH = true;           // hybrid plans: +2 % (2048) ... +5 % (8192) with
   static_assert(C == 2 || C == 4 || C == 8, "hybrid plans cover N = 2048, 4096, 8192");
   static_assert(UNITS <= 15, "named barriers 1..15");
   __host__ __device__ static constexpr int bin_of(int t, int m) { return C * ((t & 31) + 32 * m) + (t >> 5); }
@@ -156,7 +147,11 @@ struct HybridPlan {
 
 __device__ __forceinline__ float2 ld_stream(const float2 *p) {
   float2 v;
+#ifdef CRN_LD_256
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#else
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#endif
   return v;
 }
 // sc16 wire format: one 32-bit word = (I, Q) as int16.  The conversion is exact (|v| <= 32768 fits fp32);

@@ -3,6 +3,6 @@
 namespace crn {
 int launch_sense_4096(const SenseParams &prm, int window, int detector, int grid, cudaStream_t stream,
                     LaunchGeometry *geo) {
-  return launch_plan<HybridPlan<4096, 1, 3>>(prm, window, detector, grid, stream, geo);
+  return launch_plan<HybridPlan<4096, 1, 4>>(prm, window, detector, grid, stream, geo);
 }
 }  // namespace crn
