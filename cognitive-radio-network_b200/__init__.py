@@ -80,6 +80,33 @@ class SynthConfig(C.Structure):
     ]
 
 
+class AnnWeights(C.Structure):
+    """WeightIH / WeightHO with the reference's 1-based indexing (CE_Predictive_Node.hpp:66-72)."""
+    _fields_ = [("wih", (C.c_double * 6) * 5), ("who", (C.c_double * 4) * 6)]
+
+    @classmethod
+    def from_config(cls, cfg):
+        w = cls()
+        C.memmove(C.byref(w), C.addressof(cfg) + Config.ann_wih.offset, C.sizeof(cls))
+        return w
+
+    def into_config(self, cfg):
+        C.memmove(C.addressof(cfg) + Config.ann_wih.offset, C.byref(self), C.sizeof(AnnWeights))
+        return cfg
+
+    def arrays(self):
+        return (np.array([[self.wih[i][j] for j in range(6)] for i in range(5)]),
+                np.array([[self.who[j][k] for k in range(4)] for j in range(6)]))
+
+
+class AnnTrainConfig(C.Structure):
+    _fields_ = [
+        ("max_epochs", C.c_int32), ("check_every", C.c_int32), ("eta", C.c_double), ("alpha", C.c_double),
+        ("target_error", C.c_double), ("input_scale", C.c_double * 4), ("init_range", C.c_double),
+        ("seed", C.c_uint64),
+    ]
+
+
 class KernelInfo(C.Structure):
     _fields_ = [
         ("nfft", C.c_int32), ("threads_per_frame", C.c_int32), ("elems_per_thread", C.c_int32),
@@ -109,6 +136,10 @@ API = {
     "crn_synth_generate_device": (C.c_int, [C.POINTER(SynthConfig), C.c_int32, _P, C.c_int64, C.c_int64, _P, _P]),
     "crn_synth_generate_streams_device": (C.c_int, [C.POINTER(SynthConfig), C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "crn_fuse_masks_device": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+    "crn_ann_forward_device": (C.c_int, [C.POINTER(AnnWeights), C.c_double, _P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P]),
+    "crn_ann_train_config_default": (C.c_int, [C.POINTER(AnnTrainConfig)]),
+    "crn_ann_train_device": (C.c_int, [C.POINTER(AnnTrainConfig), _P, C.c_int32, _P, C.c_int64, C.POINTER(AnnWeights),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32, _P]),
     "crn_strerror": (C.c_char_p, [C.c_int]),
     "crn_last_error": (C.c_char_p, []),
     "crn_version": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -338,3 +369,33 @@ def shard_groups(ngroups, world_size, rank):
     base, rem = divmod(ngroups, world_size)
     first = rank * base + min(rank, rem)
     return first, base + (1 if rank < rem else 0)
+
+
+def ann_forward(weights, d_feat, n, feat_stride, d_out=None, d_decision=None, threshold=0.8, device=0, stream=0):
+    """Batched MLP forward pass + first-match chain (CE_Predictive_Node.cpp:214-261) over device feature rows."""
+    _check(lib.crn_ann_forward_device(C.byref(weights), threshold, _ptr(d_feat), n, feat_stride, _ptr(d_out),
+                                      _ptr(d_decision), device, C.c_void_p(stream)), "crn_ann_forward_device")
+
+
+def ann_train_config(**kw):
+    tc = AnnTrainConfig()
+    _check(lib.crn_ann_train_config_default(C.byref(tc)), "crn_ann_train_config_default")
+    for k, v in kw.items():
+        if k == "input_scale":
+            for i in range(4):
+                tc.input_scale[i] = v[i]
+        else:
+            setattr(tc, k, v)
+    return tc
+
+
+def ann_train(tc, d_feat, feat_stride, d_labels, n, weights=None, device=0, stream=0):
+    """Batch back-propagation on the GPU from labelled feature rows.  Returns (weights, final_error, epochs_run);
+    `weights` (AnnWeights) is the starting point when tc.init_range == 0."""
+    w = AnnWeights()
+    if weights is not None:
+        C.memmove(C.byref(w), C.byref(weights), C.sizeof(AnnWeights))
+    err, ep = C.c_double(0.0), C.c_int32(0)
+    _check(lib.crn_ann_train_device(C.byref(tc), _ptr(d_feat), feat_stride, _ptr(d_labels), n, C.byref(w),
+                                    C.byref(err), C.byref(ep), device, C.c_void_p(stream)), "crn_ann_train_device")
+    return w, err.value, ep.value

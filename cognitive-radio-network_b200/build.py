@@ -20,7 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
-SOURCES = ["crn_config.cpp", "crn_api.cu", "crn_synth.cu", "crn_fuse.cu", "crn_sense_n256.cu", "crn_sense_n512.cu",
+SOURCES = ["crn_config.cpp", "crn_api.cu", "crn_synth.cu", "crn_fuse.cu", "crn_ann.cu", "crn_sense_n256.cu", "crn_sense_n512.cu",
            "crn_sense_n1024.cu", "crn_sense_n2048.cu", "crn_sense_n4096.cu", "crn_sense_n8192.cu"]
 HEADERS = ["crn_internal.h", "crn_fft_regs.cuh", "crn_sense_kernel.cuh", "crn_launch.cuh",
            os.path.join(ROOT, "include", "crnsense.h")]

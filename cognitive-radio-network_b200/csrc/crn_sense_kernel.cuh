@@ -85,11 +85,19 @@ struct Plan {
   // exchange is a multi-warp barrier (measured on the generic three-pass plans: +8 % at N = 4096, +13 % at
   // N = 8192); for the one-warp-per-frame sizes plain coalesced loads plus the L2 prefetch are faster and
   // leaner in registers (1024: 599 vs 608 GS/s in the same binary, and 684 without the staging code).
+#ifdef CRN_SMALL_TMA
+  static constexpr bool TMA = true;
+#else
   static constexpr bool TMA = (T > 64);
+#endif
   // Software L2 prefetch one frame ahead.  Since the butterflies went to packed FP32 the one-warp-per-frame
   // kernels are no longer short of issue slots and hide the load latency themselves; the prefetch then only
   // adds L2 requests (measured: N = 512/1024 1-2 % faster without, N = 256 2 % faster with).
+#ifdef CRN_SMALL_PREFETCH
+  static constexpr bool PREFETCH = true;
+#else
   static constexpr bool PREFETCH = (N < 512);
+#endif
   static_assert(R0 * R1 * R2 == N, "radices must multiply to N");
   static_assert(E % R0 == 0 && E % R1 == 0 && E % R2 == 0, "E must be a multiple of every radix");
   static_assert(R0 >= 16, "first radix < 16 would bank-conflict the exchange");
@@ -505,7 +513,15 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       if constexpr (PREFETCH) {
         // the frame this team senses next: k + FT of this group, else its first frame of the next
         // group.  One frame of compute covers the DRAM latency, so the loads below hit L2.
+#ifdef CRN_PREFETCH_AHEAD
+        constexpr int AH = CRN_PREFETCH_AHEAD;
+        const int kk = k + AH * FT;
+        const int jn = (kk - K) / FT;
+        const sample_t *nx = (kk < K) ? x + AH * fstep + (SPL - 1) * t
+                                      : ((xng && fs + jn * FT < K) ? xng + jn * fstep : nullptr);
+#else
         const sample_t *nx = (k + FT < K) ? x + fstep + (SPL - 1) * t : xng;
+#endif
         if (nx) prefetch_frame_l2<E, T>(nx, (int)frame_bytes - 128 * t);
       }
       float2 a[E];
@@ -513,10 +529,14 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
         // the frame was pulled into this team's buffer (linear layout) by the bulk copy issued one frame ago
         mbar_wait(&mbars[team], tma_phase);
         tma_phase ^= 1u;
+        const sample_t *sx = reinterpret_cast<const sample_t *>(xb) + t;
+        if (full) {
 #pragma unroll
-        for (int m = 0; m < E; m++)
-          a[m] = (full || t + T * m < L) ? ld_staged(reinterpret_cast<const sample_t *>(xb) + t + T * m)
-                                         : make_float2(0.f, 0.f);
+          for (int m = 0; m < E; m++) a[m] = ld_staged(sx + T * m);
+        } else {
+#pragma unroll
+          for (int m = 0; m < E; m++) a[m] = (t + T * m < L) ? ld_staged(sx + T * m) : make_float2(0.f, 0.f);
+        }
       } else if (full) {
 #pragma unroll
         for (int m = 0; m < E; m++) a[m] = ld_stream(x + T * m);

@@ -191,6 +191,50 @@ enum crn_fusion { CRN_FUSE_OR = 0, CRN_FUSE_MAJORITY = 1, CRN_FUSE_AND = 2 };
 int crn_fuse_masks_device(const uint64_t *d_masks, int64_t nradios, int64_t nslots, int32_t nbands,
                           int32_t mode, uint64_t *d_fused, int32_t device, void *cuda_stream);
 
+/* ---- the occupancy predictor on its own (north_star: batched FMA kernel; SURVEY 8f-4: retraining) ---- */
+
+/* The 43 weights of the 4-5-3 logistic MLP with the reference's 1-based indexing (same layout as
+   crn_config.ann_wih / ann_who; CE_Predictive_Node.hpp:66-72, literals .cpp:78-120). */
+typedef struct crn_ann_weights {
+  double wih[CRN_ANN_INPUTS + 1][CRN_ANN_HIDDEN + 1];
+  double who[CRN_ANN_HIDDEN + 1][CRN_ANN_OUTPUTS + 1];
+} crn_ann_weights;
+
+/* Batched forward pass + first-match chain (CE_Predictive_Node.cpp:214-261) over n feature vectors that are
+   already in device memory: d_feat is float[n][feat_stride], inputs are columns 0..3 = NF^2, CH1, CH2, CH3
+   (.cpp:200).  d_out: double[n][3] = Output[1..3] (may be NULL); d_decision: int32[n] enum crn_decision (may
+   be NULL).  One thread per decision, fp64 FMA + exp, the reference's summation order.  Asynchronous. */
+int crn_ann_forward_device(const crn_ann_weights *w, double threshold, const float *d_feat, int64_t n,
+                           int32_t feat_stride, double *d_out, int32_t *d_decision, int32_t device,
+                           void *cuda_stream);
+
+/* On-device (re)training of the predictor from labelled feature vectors ("Array of features + label",
+   Data Generation/TODO.md:1-7).  The reference ships only the outcome of its offline training
+   ("Error = 0.000100 after 63.145737 Milion Epoch", CE_Predictive_Node.cpp:74); the trainer here is plain
+   batch back-propagation for the same network: logistic units, sum-of-squares error
+   E = 1/2 sum_p sum_k (t_pk - Output_pk)^2, update dW = eta * (-dE/dW) / n + alpha * dW_previous. */
+typedef struct crn_ann_train_config {
+  int32_t max_epochs;   /* passes over the n examples */
+  int32_t check_every;  /* epochs per CUDA-graph replay; E is read back (and target_error tested) after each */
+  double eta, alpha;    /* learning rate, momentum */
+  double target_error;  /* stop once E <= target_error (<= 0: run max_epochs) */
+  double input_scale[CRN_ANN_INPUTS]; /* the network trains on feat[i] * input_scale[i] (raw powers are
+                           1e4..1e9 and saturate every unit); the scale is folded back into wih[i][*] on
+                           return so the weights apply to raw features, as the engine feeds them.  0 -> 1 */
+  double init_range;    /* > 0: start from weights uniform in (-init_range, init_range) drawn from seed;
+                           0: start from *w as passed in (given for raw features, unfolded internally) */
+  uint64_t seed;
+} crn_ann_train_config;
+
+int crn_ann_train_config_default(crn_ann_train_config *tc);
+
+/* d_feat: float[n][feat_stride] (device), d_labels: int32[n] (device) enum crn_decision - target is 1 for the
+   labelled channel's output and 0 elsewhere (CRN_ALL_BUSY: all 0).  *w is updated in place; *final_error = E of
+   the last epoch run; *epochs_run = how many ran.  Synchronous (returns when training has finished). */
+int crn_ann_train_device(const crn_ann_train_config *tc, const float *d_feat, int32_t feat_stride,
+                         const int32_t *d_labels, int64_t n, crn_ann_weights *w, double *final_error,
+                         int32_t *epochs_run, int32_t device, void *cuda_stream);
+
 /* ---- synthetic primary-user IQ (stands in for the USRP) ----------------------- */
 
 typedef struct crn_synth_config {

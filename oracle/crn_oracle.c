@@ -375,3 +375,133 @@ void crn_oracle_synth(const crn_synth_config *sc, uint64_t stream_seed, const in
   }
   for (int t = 0; t < nt; t++) pthread_join(tid[t], NULL);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * The occupancy predictor on its own (checker for crn_ann_forward_device / crn_ann_train_device).
+ *   forward: CE_Predictive_Node.cpp:200,214-261 on given feature rows, nothing else.
+ *   train:   the reference ships only the OUTCOME of its offline training ("Error = 0.000100 after
+ *            63.145737 Milion Epoch", .cpp:74; "Array of features + label", Data Generation/TODO.md:1-7) -
+ *            no training code exists to restate, so this is the textbook batch back-propagation the GPU
+ *            trainer documents in include/crnsense.h, written as the obvious serial loops: examples in
+ *            order, E = 1/2 sum (t - Output)^2, dW = eta * (-dE/dW) / n + alpha * dW_previous.
+ * ------------------------------------------------------------------------------------------------ */
+static void ann_forward_one(const crn_ann_weights *w, const double *F, double *H, double *out) {
+  for (int j = 1; j <= CRN_ANN_HIDDEN; j++) { /* .cpp:214-220 */
+    double sum = w->wih[0][j];
+    for (int i = 1; i <= CRN_ANN_INPUTS; i++) sum += F[i] * w->wih[i][j];
+    H[j] = 1.0 / (1.0 + exp(-sum));
+  }
+  for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) { /* .cpp:229-235 */
+    double sum = w->who[0][k];
+    for (int j = 1; j <= CRN_ANN_HIDDEN; j++) sum += H[j] * w->who[j][k];
+    out[k] = 1.0 / (1.0 + exp(-sum));
+  }
+}
+
+void crn_oracle_ann_forward(const crn_ann_weights *w, double threshold, const float *feat, int64_t n,
+                            int32_t stride, double *out3, int32_t *decision) {
+  for (int64_t p = 0; p < n; p++) {
+    const float *f = feat + p * stride;
+    double F[CRN_ANN_INPUTS + 1] = {0, f[0], f[1], f[2], f[3]}; /* .cpp:200 */
+    double H[CRN_ANN_HIDDEN + 1], out[CRN_ANN_OUTPUTS + 1];
+    ann_forward_one(w, F, H, out);
+    if (out3) { out3[3 * p] = out[1]; out3[3 * p + 1] = out[2]; out3[3 * p + 2] = out[3]; }
+    if (decision) { /* .cpp:245-261 */
+      int dec = CRN_ALL_BUSY;
+      if (out[1] >= threshold) dec = CRN_CH1_OCCUPIED;
+      else if (out[2] >= threshold) dec = CRN_CH2_OCCUPIED;
+      else if (out[3] >= threshold) dec = CRN_CH3_OCCUPIED;
+      decision[p] = dec;
+    }
+  }
+}
+
+/* E and dE/dW (as -gradient sums, i.e. the direction the update follows) at weights w for scaled inputs. */
+static double ann_gradient(const crn_ann_weights *w, const double *scale, const float *feat, int32_t stride,
+                           const int32_t *labels, int64_t n, crn_ann_weights *g) {
+  memset(g, 0, sizeof(*g));
+  double E = 0.0;
+  for (int64_t p = 0; p < n; p++) {
+    const float *f = feat + p * stride;
+    double F[CRN_ANN_INPUTS + 1], H[CRN_ANN_HIDDEN + 1], out[CRN_ANN_OUTPUTS + 1], dO[CRN_ANN_OUTPUTS + 1];
+    F[0] = 1.0;
+    for (int i = 1; i <= CRN_ANN_INPUTS; i++) F[i] = (double)f[i - 1] * scale[i - 1];
+    ann_forward_one(w, F, H, out);
+    H[0] = 1.0;
+    for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) {
+      const double e = (labels[p] == k ? 1.0 : 0.0) - out[k];
+      E += 0.5 * e * e;
+      dO[k] = e * out[k] * (1.0 - out[k]);
+    }
+    for (int j = 0; j <= CRN_ANN_HIDDEN; j++)
+      for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) g->who[j][k] += H[j] * dO[k];
+    for (int j = 1; j <= CRN_ANN_HIDDEN; j++) {
+      double sdow = 0.0;
+      for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) sdow += w->who[j][k] * dO[k];
+      const double dH = sdow * H[j] * (1.0 - H[j]);
+      for (int i = 0; i <= CRN_ANN_INPUTS; i++) g->wih[i][j] += F[i] * dH;
+    }
+  }
+  return E;
+}
+
+/* Error of the network at (scaled-input) weights w: used by the finite-difference gradient test. */
+double crn_oracle_ann_error(const crn_ann_weights *w, const double *scale, const float *feat, int32_t stride,
+                            const int32_t *labels, int64_t n, crn_ann_weights *neg_grad) {
+  crn_ann_weights g;
+  const double E = ann_gradient(w, scale, feat, stride, labels, n, &g);
+  if (neg_grad) *neg_grad = g;
+  return E;
+}
+
+int crn_oracle_ann_train(const crn_ann_train_config *tc, const float *feat, int32_t stride, const int32_t *labels,
+                         int64_t n, crn_ann_weights *w, double *final_error, int32_t *epochs_run) {
+  double scale[CRN_ANN_INPUTS];
+  for (int i = 0; i < CRN_ANN_INPUTS; i++) scale[i] = tc->input_scale[i] != 0.0 ? tc->input_scale[i] : 1.0;
+  crn_ann_weights cur, dW, g;
+  memset(&cur, 0, sizeof(cur));
+  memset(&dW, 0, sizeof(dW));
+  if (tc->init_range > 0.0) { /* flat order: wih[i][j] -> i*5 + (j-1), then who[j][k] -> 25 + j*3 + (k-1) */
+    int idx = 0;
+    for (int i = 0; i <= CRN_ANN_INPUTS; i++)
+      for (int j = 1; j <= CRN_ANN_HIDDEN; j++, idx++) {
+        const double u = (double)(mix64(tc->seed + 0x9e3779b97f4a7c15ull * (uint64_t)(idx + 1)) >> 11) * (1.0 / 9007199254740992.0);
+        cur.wih[i][j] = (2.0 * u - 1.0) * tc->init_range;
+      }
+    for (int j = 0; j <= CRN_ANN_HIDDEN; j++)
+      for (int k = 1; k <= CRN_ANN_OUTPUTS; k++, idx++) {
+        const double u = (double)(mix64(tc->seed + 0x9e3779b97f4a7c15ull * (uint64_t)(idx + 1)) >> 11) * (1.0 / 9007199254740992.0);
+        cur.who[j][k] = (2.0 * u - 1.0) * tc->init_range;
+      }
+  } else {
+    cur = *w;
+    for (int i = 1; i <= CRN_ANN_INPUTS; i++)
+      for (int j = 1; j <= CRN_ANN_HIDDEN; j++) cur.wih[i][j] /= scale[i - 1];
+  }
+  double E = 0.0;
+  int epochs = 0;
+  const double inv_n = 1.0 / (double)n;
+  while (epochs < tc->max_epochs) {
+    E = ann_gradient(&cur, scale, feat, stride, labels, n, &g);
+    for (int i = 0; i <= CRN_ANN_INPUTS; i++)
+      for (int j = 1; j <= CRN_ANN_HIDDEN; j++) {
+        dW.wih[i][j] = tc->eta * g.wih[i][j] * inv_n + tc->alpha * dW.wih[i][j];
+        cur.wih[i][j] += dW.wih[i][j];
+      }
+    for (int j = 0; j <= CRN_ANN_HIDDEN; j++)
+      for (int k = 1; k <= CRN_ANN_OUTPUTS; k++) {
+        dW.who[j][k] = tc->eta * g.who[j][k] * inv_n + tc->alpha * dW.who[j][k];
+        cur.who[j][k] += dW.who[j][k];
+      }
+    epochs++;
+    /* the GPU trainer looks at E only every check_every epochs (and after the last one) */
+    if (tc->target_error > 0.0 && E <= tc->target_error &&
+        (epochs % tc->check_every == 0 || epochs == tc->max_epochs)) break;
+  }
+  for (int i = 1; i <= CRN_ANN_INPUTS; i++)
+    for (int j = 1; j <= CRN_ANN_HIDDEN; j++) cur.wih[i][j] *= scale[i - 1];
+  *w = cur;
+  if (final_error) *final_error = E;
+  if (epochs_run) *epochs_run = epochs;
+  return 0;
+}

@@ -50,6 +50,13 @@ def port():
         lib.crn_oracle_synth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         lib.crn_oracle_synth_sigma2.restype = C.c_double
         lib.crn_oracle_synth_sigma2.argtypes = [C.c_void_p]
+        lib.crn_oracle_ann_forward.restype = None
+        lib.crn_oracle_ann_forward.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.crn_oracle_ann_error.restype = C.c_double
+        lib.crn_oracle_ann_error.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        lib.crn_oracle_ann_train.restype = C.c_int
+        lib.crn_oracle_ann_train.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                             C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         _port = lib
     return _port
 
@@ -190,3 +197,39 @@ def synth(sc, nsamples, first=0, stream=0):
     iq = np.zeros(nsamples, np.complex64)
     lib.crn_oracle_synth(C.byref(sc), sseed, states.ctypes.data, iq.ctypes.data, first, nsamples)
     return iq, states
+
+
+# ---- the occupancy predictor on its own (checker for crn_ann_forward_device / crn_ann_train_device) -------------
+
+def ann_forward(weights, feat, threshold=0.8):
+    """CE_Predictive_Node.cpp:200,214-261 on feature rows (float32 [n, >=4]).  Returns (out[n,3] f64, decision[n])."""
+    feat = np.ascontiguousarray(feat, np.float32)
+    n, stride = feat.shape
+    out = np.zeros((n, 3), np.float64)
+    dec = np.zeros(n, np.int32)
+    port().crn_oracle_ann_forward(C.byref(weights), threshold, feat.ctypes.data, n, stride, out.ctypes.data, dec.ctypes.data)
+    return out, dec
+
+
+def ann_error(weights, scale, feat, labels):
+    """E = 1/2 sum (t - Output)^2 and the summed descent direction -dE/dW at (scaled-input) weights."""
+    feat = np.ascontiguousarray(feat, np.float32)
+    labels = np.ascontiguousarray(labels, np.int32)
+    scale = np.ascontiguousarray(scale, np.float64)
+    g = type(weights)()
+    E = port().crn_oracle_ann_error(C.byref(weights), scale.ctypes.data, feat.ctypes.data, feat.shape[1],
+                                    labels.ctypes.data, feat.shape[0], C.byref(g))
+    return E, g
+
+
+def ann_train(tc, feat, labels, weights):
+    """Serial batch back-propagation (the CPU statement of crn_ann_train_device).  Returns (weights, E, epochs)."""
+    feat = np.ascontiguousarray(feat, np.float32)
+    labels = np.ascontiguousarray(labels, np.int32)
+    w = type(weights)()
+    C.memmove(C.byref(w), C.byref(weights), C.sizeof(w))
+    err, ep = C.c_double(0.0), C.c_int32(0)
+    rc = port().crn_oracle_ann_train(C.byref(tc), feat.ctypes.data, feat.shape[1], labels.ctypes.data, feat.shape[0],
+                                     C.byref(w), C.byref(err), C.byref(ep))
+    assert rc == 0
+    return w, err.value, ep.value
