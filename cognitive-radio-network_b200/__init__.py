@@ -98,6 +98,21 @@ class AnnWeights(C.Structure):
         return (np.array([[self.wih[i][j] for j in range(6)] for i in range(5)]),
                 np.array([[self.who[j][k] for k in range(4)] for j in range(6)]))
 
+    def to_literals(self):
+        """The weights written like the reference's assignment block (CE_Predictive_Node.cpp:78-120); this is the
+        file format of the engine's `-m <file>` ce_args option (%.17g: the doubles round-trip exactly)."""
+        lines = ["WeightIH[%d][%d]   =        %.17g;" % (i, j, self.wih[i][j]) for j in range(1, 6) for i in range(5)]
+        lines += ["WeightHO[%d][%d]   =        %.17g;" % (j, k, self.who[j][k]) for k in range(1, 4) for j in range(6)]
+        return "\n".join(lines) + "\n"
+
+    @classmethod
+    def from_literals(cls, text):
+        import re
+        w = cls()
+        for name, a, b, v in re.findall(r"Weight(IH|HO)\[(\d+)\]\[(\d+)\]\s*=\s*([-+0-9.eE]+)\s*;", text):
+            (w.wih if name == "IH" else w.who)[int(a)][int(b)] = float(v)
+        return w
+
 
 class AnnTrainConfig(C.Structure):
     _fields_ = [

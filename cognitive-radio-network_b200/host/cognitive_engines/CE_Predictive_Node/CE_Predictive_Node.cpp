@@ -16,6 +16,9 @@
 //   -d <ms>        re-arm period         (default 100,  .hpp:30)
 //   -g <device>    CUDA device ordinal   (default 0)
 //   -o <path>      append every crn_result (binary) to this file
+//   -m <path>      MLP weights to use instead of the built-in literals, written exactly like the reference's
+//                  assignment block (.cpp:78-120): lines `WeightIH[i][j] = v;` / `WeightHO[j][k] = v;`
+//                  (e.g. the outcome of crn_ann_train_device); weights not listed keep the reference's value
 //   -q             do not print the per-decision banner
 CE_Predictive_Node::CE_Predictive_Node(int argc, char **argv, ExtensibleCognitiveRadio *_ECR) {
   ECR = _ECR;
@@ -33,11 +36,11 @@ CE_Predictive_Node::CE_Predictive_Node(int argc, char **argv, ExtensibleCognitiv
   sense = NULL;
   result_log = NULL;
   int window = CRN_WINDOW_RECT, power = 0, device = 0;
-  const char *log_path = NULL;
+  const char *log_path = NULL, *weights_path = NULL;
 
   int o;
   optind = 0;  // str2argcargv leaves it at 0 as well (src/crts.cpp:80)
-  while (argc > 0 && argv && (o = getopt(argc, argv, "n:k:w:p:d:g:o:q")) != -1) {
+  while (argc > 0 && argv && (o = getopt(argc, argv, "n:k:w:p:d:g:o:m:q")) != -1) {
     switch (o) {
       case 'n': fft_length = atoi(optarg); break;
       case 'k': fft_averaging = atoi(optarg); break;
@@ -46,6 +49,7 @@ CE_Predictive_Node::CE_Predictive_Node(int argc, char **argv, ExtensibleCognitiv
       case 'd': sensing_delay_ms = (float)atof(optarg); break;
       case 'g': device = atoi(optarg); break;
       case 'o': log_path = optarg; break;
+      case 'm': weights_path = optarg; break;
       case 'q': quiet = 1; break;
       default: break;
     }
@@ -70,7 +74,43 @@ CE_Predictive_Node::CE_Predictive_Node(int argc, char **argv, ExtensibleCognitiv
     cfg.postop = CRN_POST_SQUARE_OF_SUM;
   }
   cfg.device = device;
+  if (weights_path && load_weights(weights_path) < 0) exit(EXIT_FAILURE);  // the reference's error convention
   if (log_path) result_log = fopen(log_path, "wb");
+}
+
+// Weight file in the reference's own syntax (.cpp:78-120).  Returns the number of weights read, -1 on error.
+int CE_Predictive_Node::load_weights(const char *path) {
+  FILE *f = fopen(path, "r");
+  if (!f) {
+    printf("CE_Predictive_Node: cannot open weight file %s\n", path);
+    return -1;
+  }
+  char line[256];
+  int n = 0, lineno = 0;
+  while (fgets(line, sizeof(line), f)) {
+    lineno++;
+    int a, b;
+    double v;
+    const char *p = line;
+    while (*p == ' ' || *p == '\t') p++;
+    if (*p == '\0' || *p == '\n' || *p == '#' || (p[0] == '/' && p[1] == '/')) continue;
+    if (sscanf(p, "WeightIH[%d][%d] = %lf", &a, &b, &v) == 3) {
+      if (a < 0 || a > CRN_ANN_INPUTS || b < 1 || b > CRN_ANN_HIDDEN) goto bad;
+      cfg.ann_wih[a][b] = v;
+    } else if (sscanf(p, "WeightHO[%d][%d] = %lf", &a, &b, &v) == 3) {
+      if (a < 0 || a > CRN_ANN_HIDDEN || b < 1 || b > CRN_ANN_OUTPUTS) goto bad;
+      cfg.ann_who[a][b] = v;
+    } else {
+      goto bad;
+    }
+    n++;
+  }
+  fclose(f);
+  return n;
+bad:
+  printf("CE_Predictive_Node: %s:%d: not a WeightIH[i][j] / WeightHO[j][k] assignment: %s", path, lineno, line);
+  fclose(f);
+  return -1;
 }
 
 CE_Predictive_Node::~CE_Predictive_Node() {

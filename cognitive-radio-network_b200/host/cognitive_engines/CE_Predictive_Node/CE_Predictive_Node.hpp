@@ -35,6 +35,8 @@ private:
   crn_handle *sense;
   FILE *result_log;
 
+  int load_weights(const char *path);  // -m <file>: the reference's `WeightIH[i][j] = v;` syntax
+
 public:
   CE_Predictive_Node(int argc, char **argv, ExtensibleCognitiveRadio *_ECR);
   ~CE_Predictive_Node();

@@ -129,6 +129,7 @@ private:
   pthread_cond_t CE_cond, CE_execute_sig, rx_cond, consumed_sig, done_sig;
   bool ce_thread_running, ce_running, rx_thread_running, rx_running, capture_done;
   bool lockstep_, handoff_pending_;
+  bool ce_ever_started_;  // lock-step replay: the rx worker holds the first packet until start_ce() has been called
   IqSource *src_;
   std::complex<float> *rx_buffer;
   size_t rx_buffer_len;

@@ -36,7 +36,7 @@ size_t FileIqSource::recv(std::complex<float> *buf, size_t max_samps) {
 ExtensibleCognitiveRadio::ExtensibleCognitiveRadio()
     : ce_usrp_rx_buffer(nullptr), ce_usrp_rx_buffer_length(0), CE(nullptr), ce_timeout_ms(1000.0),
       ce_sensing_flag(0), ce_thread_running(true), ce_running(false), rx_thread_running(true),
-      rx_running(false), capture_done(false), lockstep_(false), handoff_pending_(false), src_(nullptr),
+      rx_running(false), capture_done(false), lockstep_(false), handoff_pending_(false), ce_ever_started_(false), src_(nullptr),
       rx_buffer(nullptr), rx_buffer_len(0), tx_freq_(460e6), tx_rate_(1e6), tx_gain_soft_(-12.0),
       tx_gain_uhd_(0.0), rx_freq_(460e6), rx_rate_(1e6), rx_gain_uhd_(0.0), tx_on_(false), packets_(0),
       forwarded_(0), tx_retunes_(0), executions_(0) {
@@ -84,6 +84,7 @@ void ExtensibleCognitiveRadio::set_ce(char *ce, int argc, char **argv) {
 void ExtensibleCognitiveRadio::start_ce() {
   pthread_mutex_lock(&CE_mutex);
   ce_running = true;
+  ce_ever_started_ = true;
   pthread_cond_signal(&CE_cond);
   pthread_mutex_unlock(&CE_mutex);
 }
@@ -176,8 +177,11 @@ void *ECR_rx_worker(void *arg) {
     if (ECR->ce_sensing_flag || ECR->lockstep_) {
       pthread_mutex_lock(&ECR->CE_mutex);
       if (ECR->lockstep_) {
-        // wait until the engine took the previous packet and (re-)armed sensing
-        while ((ECR->handoff_pending_ || !ECR->ce_sensing_flag) && ECR->ce_thread_running && ECR->ce_running)
+        // wait until the engine took the previous packet and (re-)armed sensing.  start_rx() precedes
+        // start_ce() (src/crts_cognitive_radio.cpp:810-812), so "CE not started YET" must wait as well - or a
+        // short capture is drained before the engine ever runs; a CE that was stopped again lets packets drop.
+        while ((ECR->handoff_pending_ || !ECR->ce_sensing_flag) && ECR->ce_thread_running &&
+               (ECR->ce_running || !ECR->ce_ever_started_))
           pthread_cond_wait(&ECR->consumed_sig, &ECR->CE_mutex);
       }
       if (ECR->ce_sensing_flag) {  // re-check under the mutex, as upstream does (cpp:1313)

@@ -158,3 +158,56 @@ def test_replayed_capture_matches_reference_engine_fixtures(crn, replay, tmp_pat
     last_tx = [crn.TX_FREQ_FOR_DECISION[int(d)] for d in dec if crn.TX_FREQ_FOR_DECISION[int(d)]]
     if last_tx:
         assert "final tx_freq=%.0f Hz" % last_tx[-1] in r.stdout
+
+
+def test_weight_file_syntax_round_trips_and_bad_files_are_fatal(crn, replay, tmp_path):
+    """`-m <file>` takes the reference's own assignment syntax (CE_Predictive_Node.cpp:78-120)."""
+    w = crn.AnnWeights.from_config(crn.config_reference())
+    text = w.to_literals()
+    assert "WeightIH[0][1]   =        -0.18820799999999999;" in text and text.count("Weight") == 43
+    w2 = crn.AnnWeights.from_literals(text)
+    assert all(np.array_equal(a, b) for a, b in zip(w.arrays(), w2.arrays()))
+    # the parser also reads the block exactly as upstream formats it
+    up = "  WeightIH[4][5]   =        0.609384;\n  WeightHO[0][1]   =        -7.033320;\n"
+    w3 = crn.AnnWeights.from_literals(up)
+    assert w3.wih[4][5] == 0.609384 and w3.who[0][1] == -7.033320
+    iq = tmp_path / "z.c64"
+    np.zeros(512 * 10, np.complex64).tofile(iq)
+    bad = tmp_path / "bad_weights.txt"
+    bad.write_text("WeightIH[9][1] = 1.0;\n")
+    r = run(replay, ["--scenario", SCENARIO, "--node", "2", "--iq", str(iq), "--ce-args", "-d 0 -q -m %s" % bad])
+    assert r.returncode != 0 and "bad_weights.txt:1" in r.stdout
+    r = run(replay, ["--scenario", SCENARIO, "--node", "2", "--iq", str(iq), "--ce-args", "-d 0 -q -m /nonexistent"])
+    assert r.returncode != 0 and "cannot open weight file" in r.stdout
+
+
+@pytest.mark.gpu
+def test_engine_follows_a_weight_file(crn, replay, tmp_path):
+    """Weights handed to the plugin through ce_args reach the GPU: the reference's own literals written to a file
+    reproduce the fixture, and a file that flips the sign of the output layer changes the decisions the way the
+    CPU statement of the engine says it should."""
+    import oracle as O
+    g = np.load(os.path.join(GOLDEN, "ref_markov_L512.npz"))
+    iq = tmp_path / "cap.c64"
+    g["iq"].astype(np.complex64).tofile(iq)
+    nd = len(g["decision"])
+    w = crn.AnnWeights.from_config(crn.config_reference())
+    flipped = crn.AnnWeights.from_literals(w.to_literals())
+    for j in range(6):
+        for k in range(1, 4):
+            flipped.who[j][k] = -flipped.who[j][k]
+    for name, weights in (("same", w), ("flipped", flipped)):
+        wf = tmp_path / (name + ".txt")
+        wf.write_text("// weights written by the test\n" + weights.to_literals())
+        log = tmp_path / (name + ".bin")
+        r = run(replay, ["--scenario", SCENARIO, "--node", "2", "--iq", str(iq), "--packet-len", "512",
+                         "--ce-args", "-d 0 -q -o %s -m %s" % (log, wf)])
+        assert r.returncode == 0, r.stdout + r.stderr
+        res = (crn.Result * nd).from_buffer_copy(open(log, "rb").read())
+        feat, ann, dec, _ = crn.results_to_arrays(res, 4)
+        oann, odec = O.ann_forward(weights, g["feat"])
+        assert np.abs(ann - oann).max() <= 1e-5 and np.array_equal(dec, odec)
+        if name == "same":
+            assert np.array_equal(dec, g["decision"])
+        else:
+            assert not np.array_equal(dec, g["decision"])
