@@ -82,10 +82,10 @@ struct Plan {
   // spectrum bin held in accumulator register m of team thread t after the last pass
   __host__ __device__ static constexpr int bin_of(int t, int m) { return t + T * m; }
   // Bulk-copy (TMA) staging of the next frame pays off where a frame spans several warps and every
-  // exchange is a multi-warp barrier (measured on the generic three-pass plans: +8 % at N = 4096, +13 % at
-  // N = 8192); for the one-warp-per-frame sizes plain coalesced loads plus the L2 prefetch are faster and
-  // leaner in registers (1024: 599 vs 608 GS/s in the same binary, and 684 without the staging code).
-#ifdef CRN_SMALL_TMA
+  // exchange is a multi-warp barrier (the hybrid plans); for the one-warp-per-frame sizes plain coalesced loads
+  // are faster (same binary on the B200, packed-FP32 codelets: N = 1024 735.6 GS/s staged vs 751.7 plain,
+  // N = 512 712 vs 770: the staged frame costs one more shared-memory read).
+#ifdef CRN_SMALL_TMA  // A/B switch (build.py --variant): bulk-copy staging for the one-warp-per-frame plans too
   static constexpr bool TMA = true;
 #else
   static constexpr bool TMA = (T > 64);
@@ -93,7 +93,7 @@ struct Plan {
   // Software L2 prefetch one frame ahead.  Since the butterflies went to packed FP32 the one-warp-per-frame
   // kernels are no longer short of issue slots and hide the load latency themselves; the prefetch then only
   // adds L2 requests (measured: N = 512/1024 1-2 % faster without, N = 256 2 % faster with).
-#ifdef CRN_SMALL_PREFETCH
+#ifdef CRN_SMALL_PREFETCH  // A/B switch: L2 prefetch one frame ahead at every size
   static constexpr bool PREFETCH = true;
 #else
   static constexpr bool PREFETCH = (N < 512);
@@ -513,15 +513,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       if constexpr (PREFETCH) {
         // the frame this team senses next: k + FT of this group, else its first frame of the next
         // group.  One frame of compute covers the DRAM latency, so the loads below hit L2.
-#ifdef CRN_PREFETCH_AHEAD
-        constexpr int AH = CRN_PREFETCH_AHEAD;
-        const int kk = k + AH * FT;
-        const int jn = (kk - K) / FT;
-        const sample_t *nx = (kk < K) ? x + AH * fstep + (SPL - 1) * t
-                                      : ((xng && fs + jn * FT < K) ? xng + jn * fstep : nullptr);
-#else
         const sample_t *nx = (k + FT < K) ? x + fstep + (SPL - 1) * t : xng;
-#endif
         if (nx) prefetch_frame_l2<E, T>(nx, (int)frame_bytes - 128 * t);
       }
       float2 a[E];
