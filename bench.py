@@ -428,6 +428,12 @@ def main():
                     help="default = BASELINE configs[1] (the contract's bench line); others = remaining BASELINE configs")
     args = ap.parse_args()
     ACTIVE["name"] = args.workload
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 behind
+    # Python's back (NCCL prints its version banner there under NCCL_DEBUG=VERSION) are sent to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
