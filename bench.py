@@ -377,7 +377,8 @@ def run_ours(args):
     t1 = time.perf_counter()
     e2e_sec = cdist.max_over_ranks(t1 - t0, dev)
     hf, ha, hd, _ = crn.results_to_arrays(res, cfg.nbands)
-    e2e_ok = bool(np.array_equal(hf, d_feat.cpu().numpy()) and np.array_equal(hd, d_dec.cpu().numpy()))
+    # the host path launches 128-group chunks whose groups are split over several CTAs: equal to fp32 rounding
+    e2e_ok = bool(np.allclose(hf, d_feat.cpu().numpy(), rtol=2e-6, atol=0) and np.array_equal(hd, d_dec.cpu().numpy()))
     e2e = {"value": world * nsamp * e2e_steps / e2e_sec / 1e9, "unit": UNIT,
            "h2d_bytes_per_step": nsamp * sample_bytes, "d2h_bytes_per_step": ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8),
            "steps": e2e_steps, "path": "crn_sense_batch_host (C-ABI), pinned host IQ, 64 MiB double-buffered chunks; wall clock, max over ranks",
@@ -415,6 +416,76 @@ def run_ours(args):
     return 0
 
 
+def run_sweep(args):
+    """BASELINE configs[4]: FFT size 256..8192 x batch 1e3..1e6 frames (Welch K=64 + ANN; N=256 uses the 16-channel
+    energy plan), device-resident, every rank its own batch (weak), max over ranks; the reference CPU path (oracle
+    port, all host threads, bounded sample) timed beside every FFT size on rank 0.  ONE JSON line with all rows."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import crn_b200 as crn
+    import importlib
+    cdist = importlib.import_module("crn_b200.dist")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --sweep: no CUDA device; libcrnsense has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    peak, peak_src = measured_peak()
+    max_samples = 2 * 10 ** 9                       # 16 GB of IQ per GPU at most (8192 x 1e6 is capped)
+    d_iq = torch.empty(max_samples, 2, dtype=torch.float32, device=dev)
+    crn.synth_generate(crn.synth_config(65536, dwell_groups=64, snr_db=10.0, seed=12), d_iq, rank * max_samples,
+                       max_samples, None, local_rank, stream)
+    torch.cuda.synchronize()
+    rows = []
+    for n in (256, 512, 1024, 2048, 4096, 8192):
+        cfg = crn.config_welch(n, NAVG) if n >= 512 else crn.config_wideband(n, NAVG, 16)
+        gs = cfg.group_samples
+        cpu = None
+        if rank == 0 and not args.no_cpu:          # reference CPU path beside this FFT size (bounded sample)
+            take = min(max_samples, 64 * 10 ** 6)
+            iq_host = d_iq[:take].cpu().numpy().view(np.complex64).ravel()
+            cpu = cpu_leg(crn, cfg, iq_host, min(args.cpu_seconds, 2.0))
+        with crn.Sensor(cfg, device=local_rank) as sensor:
+            info = sensor.kernel_info()
+            for frames in (10 ** 3, 10 ** 4, 10 ** 5, 10 ** 6):
+                ng = max(1, min(frames // cfg.navg, max_samples // gs))
+                d_feat = torch.empty(ng, cfg.nbands, dtype=torch.float32, device=dev)
+                d_ann = torch.empty(ng, 3, dtype=torch.float64, device=dev)
+                d_dec = torch.empty(ng, dtype=torch.int32, device=dev)
+                for _ in range(max(args.warmup, 3)):
+                    sensor.sense_device(d_iq, ng, d_feat, d_ann, d_dec, None, stream)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    sensor.sense_device(d_iq, ng, d_feat, d_ann, d_dec, None, stream)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = cdist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+                gsps = world * ng * gs / ms / 1e6
+                rows.append({"nfft": n, "frames_per_gpu": ng * cfg.navg, "capped": ng * cfg.navg < frames,
+                             "samples_per_gpu": ng * gs, "ms_per_launch": ms, "gsamples_s": gsps,
+                             "frac_of_hbm_peak": gsps * 8 / (peak * world), "kernel": info["name"],
+                             "cpu_gsamples_s": cpu["value"] if cpu else None, "cpu_cores": cpu["cores"] if cpu else None})
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "scaling": "weak",
+                          "data": "synthetic", "dtype": "f32", "hbm_peak_gbs": peak, "peak_source": peak_src,
+                          "config": {"workload": "configs[4]: FFT-size sweep 256-8192 points x batch 1e3-1e6 frames, "
+                                                 "64-frame Welch average + ANN, beside the reference CPU path on host cores"},
+                          "sweep": rows}), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,6 +495,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: FFT size x batch frames, one JSON line with all rows")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
                     help="default = BASELINE configs[1] (the contract's bench line); others = remaining BASELINE configs")
     args = ap.parse_args()
@@ -436,6 +508,8 @@ def main():
     sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         return run_reference(args)
+    if args.sweep:
+        return run_sweep(args)
     return run_ours(args)
 
 

@@ -58,6 +58,11 @@ struct crn_handle {
   crn::SenseParams base;  // everything but iq / outputs / ngroups
   float4 *d_tw = nullptr;
   float2 *d_win = nullptr;
+  // group splitting (crn_sense_kernel.cuh): per-part segment sums and arrival counters, grown on demand
+  int max_split = 16;       // CRN_SPLIT=<n> (read once at create) caps it; 1 disables splitting
+  float *d_scratch = nullptr;
+  int *d_gcount = nullptr;
+  size_t scratch_cap = 0, gcount_cap = 0;
   cudaStream_t stream = nullptr;     // streaming path + batch_host compute
   cudaStream_t copy_stream = nullptr;
   int64_t launches = 0;
@@ -175,12 +180,74 @@ int pick_upg(int units, int teams_per_unit, int K) {
   return best;
 }
 
-int grid_for(const crn_handle *h, int64_t ngroups) {
+int grid_for(const crn_handle *h, int64_t nwork) {
   int64_t g = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
   const int64_t gl = h->base.upg > 0 ? h->geo.units / h->base.upg : 1;  // groups a CTA works on at a time
-  const int64_t need = (ngroups + gl - 1) / gl;
+  const int64_t need = (nwork + gl - 1) / gl;
   if (need < g) g = need;
   return (int)(g < 1 ? 1 : g);
+}
+
+// Work items per group for this launch (CTA epilogue only): the power of two <= max_split, with whole frames per
+// team and item, that minimises rounds x (frames per team and item + epilogue), the epilogue counted as two
+// frames.  Many groups -> 1 (nothing to gain); one decision on the streaming path -> as many items as K allows.
+int pick_split(const crn_handle *h, int64_t ngroups) {
+  if (h->base.upg != 0) return 1;
+  const int K = h->cfg.navg, teams = h->geo.teams;
+  const int64_t ctas = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
+  int best = 1;
+  double best_cost = 1e300;
+  for (int sp = 1; sp <= h->max_split; sp *= 2) {
+    if (K % (sp * teams)) break;
+    const int64_t rounds = (ngroups * sp + ctas - 1) / ctas;
+    const double cost = (double)rounds * ((double)(K / (sp * teams)) + 2.0);
+    if (cost < best_cost * (1.0 - 1e-9)) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  return best;
+}
+
+// Scratch rows and arrival counters for a split launch.  Growing them waits for the device: earlier launches of
+// this handle may still be using the old buffers.
+int ensure_split_buffers(crn_handle *h, int64_t ngroups, int split) {
+  const size_t need_s = (size_t)ngroups * split * h->cfg.nsegs, need_c = (size_t)ngroups;
+  if (need_s <= h->scratch_cap && need_c <= h->gcount_cap) return CRN_OK;
+  CRN_CUDA(cudaDeviceSynchronize());
+  if (need_s > h->scratch_cap) {
+    cudaFree(h->d_scratch);
+    h->d_scratch = nullptr;
+    h->scratch_cap = 0;
+    CRN_CUDA(cudaMalloc(&h->d_scratch, sizeof(float) * need_s));
+    h->scratch_cap = need_s;
+  }
+  if (need_c > h->gcount_cap) {
+    cudaFree(h->d_gcount);
+    h->d_gcount = nullptr;
+    h->gcount_cap = 0;
+    CRN_CUDA(cudaMalloc(&h->d_gcount, sizeof(int) * need_c));
+    CRN_CUDA(cudaMemset(h->d_gcount, 0, sizeof(int) * need_c));
+    h->gcount_cap = need_c;
+  }
+  return CRN_OK;
+}
+
+// Fills the launch-shape dependent fields of p (split, scratch) and returns the grid size through *grid.
+int shape_launch(crn_handle *h, crn::SenseParams &p, int64_t ngroups, int *grid) {
+  p.split = pick_split(h, ngroups);
+  p.kp = h->cfg.navg / p.split;
+  p.nwork = ngroups * p.split;
+  p.scratch = nullptr;
+  p.gcount = nullptr;
+  if (p.split > 1) {
+    int st = ensure_split_buffers(h, ngroups, p.split);
+    if (st != CRN_OK) return st;
+    p.scratch = h->d_scratch;
+    p.gcount = h->d_gcount;
+  }
+  *grid = grid_for(h, ngroups * p.split);
+  return CRN_OK;
 }
 
 int launch(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat, double *d_ann,
@@ -196,7 +263,10 @@ int launch(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat, doub
   // bulk-copy (TMA) staging needs 16-byte aligned frame addresses and sizes; anything else uses plain loads
   p.use_tma = (p.upg == 0) && h->allow_tma && ((reinterpret_cast<uintptr_t>(d_iq) & 15) == 0) &&
               ((h->stride * h->sample_bytes) % 16 == 0) && ((h->cfg.frame_len * h->sample_bytes) % 16 == 0);
-  int st = h->launch(p, h->cfg.window, h->cfg.detector, grid_for(h, ngroups), s, nullptr);
+  int grid = 1;
+  int st = shape_launch(h, p, ngroups, &grid);
+  if (st != CRN_OK) return st;
+  st = h->launch(p, h->cfg.window, h->cfg.detector, grid, s, nullptr);
   if (st == CRN_OK) h->launches++;
   return st;
 }
@@ -317,6 +387,8 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     const bool long_even_groups = (cfg->navg % teams == 0) && (cfg->navg / teams >= 8);
     const char *no_tma = getenv("CRN_NO_TMA");
     h->allow_tma = !(no_tma && no_tma[0] == '1');
+    const char *cap = getenv("CRN_SPLIT");  // development override: largest split (1 = never split a group)
+    if (cap && atoi(cap) >= 1) h->max_split = atoi(cap);
     const char *force = getenv("CRN_EPI");  // "cta" | "unit": development override
     bool cta = long_even_groups;
     if (force && !strcmp(force, "cta")) cta = true;
@@ -364,6 +436,8 @@ int crn_destroy(crn_handle *h) {
   }
   cudaFree(h->d_tw);
   cudaFree(h->d_win);
+  cudaFree(h->d_scratch);
+  cudaFree(h->d_gcount);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -402,7 +476,10 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   p.decision = s.res.d_dec;
   p.mask = s.res.d_mask;
   p.ngroups = 1;
-  int st = h->launch(p, h->cfg.window, h->cfg.detector, 1, h->stream, nullptr);
+  int grid = 1;
+  int st = shape_launch(h, p, 1, &grid);  // one decision: its K frames are dealt to several CTAs
+  if (st != CRN_OK) return st;
+  st = h->launch(p, h->cfg.window, h->cfg.detector, grid, h->stream, nullptr);
   if (st != CRN_OK) return st;
   h->launches++;
   st = fetch_results_async(s.res, 1, h->cfg.nbands, h->stream);

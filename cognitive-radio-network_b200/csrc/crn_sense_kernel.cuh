@@ -29,6 +29,12 @@
 // barrier in the steady state: each unit reduces its own accumulators to per-segment partial sums, and
 // the last unit of a group to arrive (shared-memory counter) combines them, runs the MLP and writes the
 // decision while the others already work on their next group.
+//
+// Group splitting (CTA epilogue only).  With few groups per launch - one decision on the streaming path, a tail
+// round that fills half the GPU - a whole group per CTA leaves SMs idle.  The host may therefore deal a group's
+// K frames to `split` work items of K/split consecutive frames; each item leaves its per-segment sums in a
+// scratch row, and the item that arrives last (one atomic per item, the classic threadfence reduction) adds the
+// rows in part order and takes the decision.  The order of additions is fixed by (K, split), never by timing.
 #pragma once
 #include <cstdint>
 #include <type_traits>
@@ -54,6 +60,11 @@ struct SenseParams {
   int nbands, nsegs, postop, decide;
   int upg;               // reduction units per decision group (divides UNITS); 0 = CTA-wide epilogue
   int use_tma;           // 1: stage frames with cp.async.bulk (needs 16-byte aligned frames, CTA epilogue)
+  int split;             // CTA epilogue: a group's K frames are dealt to `split` work items (K % (split*TEAMS) == 0)
+  int kp;                // K / split: frames per work item
+  long long nwork;       // ngroups * split
+  float *scratch;        // [ngroups][split][nsegs] per-part segment sums (split > 1)
+  int *gcount;           // [ngroups] parts arrived, zero between launches (split > 1)
   int sc16;              // IQ buffers hold int16 pairs (4 B/sample) instead of float pairs
   unsigned acc_mask;     // bit m set: some band segment reads a bin held in accumulator register m
   double threshold, energy_factor;
@@ -489,31 +500,40 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
 
   const int L = prm.L, K = prm.K;
   const bool full = (L == N);
+  // Work items (see "Group splitting" above).  The all-bins kernels sit exactly at the register cap, so the item
+  // bookkeeping (split, frames per item, item count) stays in the parameter bank - operands, not registers - and
+  // group / slice are derived from the item index only where they are needed.
+  const int KP = (EPI == EPI_CTA) ? prm.kp : K;    // frames per work item
   const long long gstep = (long long)gridDim.x * GL;
   const unsigned frame_bytes = (unsigned)L * (unsigned)sizeof(sample_t);
+  // first frame this team senses in work item w (group w / split, frames [slice*KP, (slice+1)*KP))
+  auto first_frame = [&](long long w) -> const sample_t * {
+    const int S = (EPI == EPI_CTA) ? prm.split : 1;
+    const long long g = (S == 1) ? w : w / S;
+    const int slice = (int)(w - g * S);
+    return iq + ((size_t)g * (size_t)K + (size_t)slice * (size_t)KP + (size_t)fs) * (size_t)prm.stride;
+  };
   unsigned tma_phase = 0;
-  if (tma && t == 0 && fs < K && (long long)blockIdx.x * GL + gl < prm.ngroups)  // first frame of the first group
-    tma_load_frame(xb, iq + (((size_t)blockIdx.x * GL + gl) * (size_t)K + (size_t)fs) * (size_t)prm.stride,
-                   frame_bytes, &mbars[team]);
+  if (tma && t == 0 && fs < KP && (long long)blockIdx.x * GL + gl < prm.nwork)  // first item's first frame
+    tma_load_frame(xb, first_frame((long long)blockIdx.x * GL + gl), frame_bytes, &mbars[team]);
 
   int it = 0;
-  for (long long g = (long long)blockIdx.x * GL + gl; g < prm.ngroups; g += gstep, it++) {
+  for (long long w = (long long)blockIdx.x * GL + gl; w < prm.nwork; w += gstep, it++) {
     float acc[E];
 #pragma unroll
     for (int m = 0; m < E; m++) acc[m] = 0.0f;
 
-    // frame pointers advance by plain 64-bit adds inside the loop; the multiplications happen once per group
+    // frame pointers advance by plain 64-bit adds inside the loop; the multiplications happen once per item
     const size_t fstep = (size_t)FT * (size_t)prm.stride;  // samples between this team's frames
-    const sample_t *x = iq + ((size_t)g * (size_t)K + (size_t)fs) * (size_t)prm.stride + t;
-    // first frame this team senses in the CTA's next group (prefetch target at the group boundary);
+    const sample_t *x = first_frame(w) + t;
+    // first frame this team senses in the CTA's next item (prefetch target at the item boundary);
     // "+ (SPL-1) t" turns the per-thread sample pointer into a per-thread 128-byte line pointer
-    const sample_t *xng =
-        (g + gstep < prm.ngroups) ? x + (size_t)gstep * (size_t)K * (size_t)prm.stride + (SPL - 1) * t : nullptr;
-    for (int k = fs; k < K; k += FT, x += fstep) {
+    const sample_t *xng = (w + gstep < prm.nwork) ? first_frame(w + gstep) + t + (SPL - 1) * t : nullptr;
+    for (int k = fs; k < KP; k += FT, x += fstep) {
       if constexpr (PREFETCH) {
         // the frame this team senses next: k + FT of this group, else its first frame of the next
         // group.  One frame of compute covers the DRAM latency, so the loads below hit L2.
-        const sample_t *nx = (k + FT < K) ? x + fstep + (SPL - 1) * t : xng;
+        const sample_t *nx = (k + FT < KP) ? x + fstep + (SPL - 1) * t : xng;
         if (nx) prefetch_frame_l2<E, T>(nx, (int)frame_bytes - 128 * t);
       }
       float2 a[E];
@@ -555,7 +575,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
         __syncwarp();  // the region is rewritten in padded layout below
         reg_pass_first<E, 32, 32, false>(a, winp, lane);
         exchange<E, 32, 32, 1, 5>(a, wb, lane, 0);
-        if (tma && k + FT < K) {
+        if (tma && k + FT < KP) {
           team_sync<T>(team);  // every warp of the team has gathered its points: the regions are idle
           if (t == 0) tma_load_frame(xb, x + fstep, frame_bytes, &mbars[team]);
         }
@@ -567,7 +587,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       // after the frame's last exchange the buffer is free: start pulling this team's next frame now, so
       // the copy flies under the remaining butterflies and the accumulate
       auto stage_next = [&]() {
-        if (tma && k + FT < K) {
+        if (tma && k + FT < KP) {
           team_sync<T>(team);  // every lane has gathered its points
           if (t == 0) tma_load_frame(xb, x + fstep, frame_bytes, &mbars[team]);  // (t == 0: x is the frame base)
         }
@@ -597,6 +617,9 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       });
     }
 
+    const int S = (EPI == EPI_CTA) ? prm.split : 1;
+    const long long g = (S == 1) ? w : w / S;  // decision group of this item
+    const int ipart = (int)(w - g * S);        // which K/S-frame slice of it
     if constexpr (EPI == EPI_CTA) {
       // ---- per-group epilogue, CTA-wide ----------------------------------------------------------------
       float *segsum = segpart;  // [CRN_MAX_SEGS]
@@ -638,22 +661,45 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       }
       __syncthreads();
       if (tid < 32) {
-        for (int b = tid; b < prm.nbands; b += 32) {
-          float m = 0.0f;
-          for (int s = 0; s < prm.nsegs; s++)
-            if (prm.seg_band[s] == b) m += segsum[s];
-          m *= prm.invK;
-          const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
-          featbuf[b] = f;
-          prm.feat[(size_t)g * prm.nbands + b] = (prm.postop == CRN_POST_SUM_DB) ? 10.0f * log10f(f) : f;
+        bool decide = true;
+        if (S > 1) {
+          // publish this item's segment sums; the item that arrives last adds the rows in part order
+          float *row = prm.scratch + ((size_t)g * S + ipart) * (size_t)prm.nsegs;
+          for (int sg = tid; sg < prm.nsegs; sg += 32) __stcg(row + sg, segsum[sg]);
+          __threadfence();
+          __syncwarp();
+          int last = 0;
+          if (tid == 0) last = (atomicAdd(prm.gcount + g, 1) == S - 1);
+          decide = __shfl_sync(0xffffffffu, last, 0) != 0;
+          if (decide) {
+            __threadfence();
+            const float *rows = prm.scratch + (size_t)g * S * (size_t)prm.nsegs;
+            for (int sg = tid; sg < prm.nsegs; sg += 32) {
+              float v = 0.0f;
+              for (int q = 0; q < S; q++) v += __ldcg(rows + (size_t)q * prm.nsegs + sg);
+              segsum[sg] = v;
+            }
+            if (tid == 0) prm.gcount[g] = 0;  // zero again for the next launch
+            __syncwarp();
+          }
         }
-        __syncwarp();
-        decide_and_store(prm, featbuf, g, tid);
+        if (decide) {
+          for (int b = tid; b < prm.nbands; b += 32) {
+            float m = 0.0f;
+            for (int sg = 0; sg < prm.nsegs; sg++)
+              if (prm.seg_band[sg] == b) m += segsum[sg];
+            m *= prm.invK;
+            const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
+            featbuf[b] = f;
+            prm.feat[(size_t)g * prm.nbands + b] = (prm.postop == CRN_POST_SUM_DB) ? 10.0f * log10f(f) : f;
+          }
+          __syncwarp();
+          decide_and_store(prm, featbuf, g, tid);
+        }
       }
-      // the exchange buffers are free again (the last barrier above): pull the first frame of the next group
-      if (tma && t == 0 && fs < K && g + gstep < prm.ngroups)
-        tma_load_frame(xb, iq + ((size_t)(g + gstep) * (size_t)K + (size_t)fs) * (size_t)prm.stride,
-                       frame_bytes, &mbars[team]);
+      // the exchange buffers are free again (the last barrier above): pull the first frame of the next item
+      if (tma && t == 0 && fs < KP && w + gstep < prm.nwork)
+        tma_load_frame(xb, first_frame(w + gstep), frame_bytes, &mbars[team]);
       // nothing after the last barrier reads the exchange buffers, so the next group may start at once;
       // segsum/featbuf are rewritten only after the next group's barriers.
     } else {

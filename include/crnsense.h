@@ -177,6 +177,10 @@ int crn_sense_batch_host(crn_handle *h, const void *iq, int64_t ngroups, crn_res
    legacy default stream).  Output arrays are device pointers; any of d_ann / d_decision / d_mask may
    be NULL.  d_feat: float[ngroups][nbands]; d_ann: double[ngroups][3]; d_decision: int32[ngroups];
    d_mask: uint64[ngroups].  IQ is read from HBM exactly once; only these features are written. */
+/* Reproducibility: a launch is deterministic - the same handle configuration and the same ngroups give the same
+   bits, every time.  Launches of different shapes (one 300-group batch vs chunks of 128, the one-decision
+   launches of the streaming path) may deal a group's frames to a different number of CTAs, which re-associates
+   the fp32 band sums: such results agree to fp32 rounding (~1e-7 relative), far inside the 1e-4 parity bar. */
 int crn_sense_batch_device(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat,
                            double *d_ann, int32_t *d_decision, uint64_t *d_mask, void *cuda_stream);
 
