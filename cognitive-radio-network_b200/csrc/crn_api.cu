@@ -60,6 +60,10 @@ struct crn_handle {
   float2 *d_win = nullptr;
   // group splitting (crn_sense_kernel.cuh): per-part segment sums and arrival counters, grown on demand
   int max_split = 16;       // CRN_SPLIT=<n> (read once at create) caps it; 1 disables splitting
+  // Streaming path: from 2 MiB per decision the kernel reads the pinned slot over PCIe itself (transfer and FFTs
+  // overlap frame by frame: 137 -> 127 us at 4 MiB); below that a host->device copy ahead of the kernel is quicker
+  // (40 vs 43 us at 512 KiB, 27 vs 30 us at 40 KiB).  CRN_RING_COPY=1 / 0 forces the copy / the direct read (A/B).
+  bool ring_zero_copy = false;
   float *d_scratch = nullptr;
   int *d_gcount = nullptr;
   size_t scratch_cap = 0, gcount_cap = 0;
@@ -387,6 +391,10 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     const bool long_even_groups = (cfg->navg % teams == 0) && (cfg->navg / teams >= 8);
     const char *no_tma = getenv("CRN_NO_TMA");
     h->allow_tma = !(no_tma && no_tma[0] == '1');
+    const char *rc = getenv("CRN_RING_COPY");
+    h->ring_zero_copy = (rc && (rc[0] == '0' || rc[0] == '1'))
+                            ? rc[0] == '0'
+                            : h->sample_bytes * (size_t)cfg->navg * cfg->frame_len >= ((size_t)2 << 20);
     const char *cap = getenv("CRN_SPLIT");  // development override: largest split (1 = never split a group)
     if (cap && atoi(cap) >= 1) h->max_split = atoi(cap);
     const char *force = getenv("CRN_EPI");  // "cta" | "unit": development override
@@ -467,14 +475,24 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   // K-th frame: ship the slot and enqueue the fused kernel (stream ordered, non blocking)
   CRN_CUDA(cudaSetDevice(h->device));
   const size_t slot_bytes = h->sample_bytes * (size_t)h->cfg.navg * h->cfg.frame_len;
-  CRN_CUDA(cudaMemcpyAsync(s.d_iq, s.h_iq, slot_bytes, cudaMemcpyHostToDevice, h->stream));
   crn::SenseParams p = h->base;
   p.stride = h->cfg.frame_len;  // ring slots are packed
-  p.iq = reinterpret_cast<const float2 *>(s.d_iq);
-  p.feat = s.res.d_feat;
-  p.ann = s.res.d_ann;
-  p.decision = s.res.d_dec;
-  p.mask = s.res.d_mask;
+  if (h->ring_zero_copy) {
+    // every sample is read exactly once, so the kernel can pull it across PCIe itself: transfer and FFTs overlap
+    // frame by frame and there is no copy -> launch hand-over on the stream
+    void *dp = nullptr;
+    CRN_CUDA(cudaHostGetDevicePointer(&dp, s.h_iq, 0));
+    p.iq = reinterpret_cast<const float2 *>(dp);
+  } else {
+    CRN_CUDA(cudaMemcpyAsync(s.d_iq, s.h_iq, slot_bytes, cudaMemcpyHostToDevice, h->stream));
+    p.iq = reinterpret_cast<const float2 *>(s.d_iq);
+  }
+  // the decision's 52..300 bytes are written by the kernel straight into the slot's page-locked host mirror
+  // (pinned memory is device-addressable): no device->host copies queue up behind the kernel
+  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.feat, s.res.h_feat, 0));
+  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.ann, s.res.h_ann, 0));
+  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.decision, s.res.h_dec, 0));
+  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.mask, s.res.h_mask, 0));
   p.ngroups = 1;
   int grid = 1;
   int st = shape_launch(h, p, 1, &grid);  // one decision: its K frames are dealt to several CTAs
@@ -482,8 +500,6 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   st = h->launch(p, h->cfg.window, h->cfg.detector, grid, h->stream, nullptr);
   if (st != CRN_OK) return st;
   h->launches++;
-  st = fetch_results_async(s.res, 1, h->cfg.nbands, h->stream);
-  if (st != CRN_OK) return st;
   CRN_CUDA(cudaEventRecord(s.done, h->stream));
   s.state = 1;
   h->inflight++;
