@@ -35,10 +35,20 @@ struct ResultBuf {
   int64_t cap = 0;
 };
 
+// Scratch of a split launch (crn_sense_kernel.cuh "Group splitting"): per-part segment sums and per-group arrival
+// counters (zero between launches).  Kernels that may overlap on the GPU must not share one: every ring slot,
+// the batch-host pipeline and the batch-device entry point own theirs.
+struct SplitBuf {
+  float *d_scratch = nullptr;
+  int *d_gcount = nullptr;
+  size_t scratch_cap = 0, gcount_cap = 0;
+};
+
 struct RingSlot {
   unsigned char *h_iq = nullptr;  // pinned [K][L] samples in cfg.iq_format
   unsigned char *d_iq = nullptr;  // device mirror
   ResultBuf res;
+  SplitBuf split;
   cudaEvent_t done = nullptr;
   uint64_t first_frame = 0;
   int state = 0;  // 0 free/filling, 1 in flight
@@ -64,9 +74,7 @@ struct crn_handle {
   // overlap frame by frame: 137 -> 127 us at 4 MiB); below that a host->device copy ahead of the kernel is quicker
   // (40 vs 43 us at 512 KiB, 27 vs 30 us at 40 KiB).  CRN_RING_COPY=1 / 0 forces the copy / the direct read (A/B).
   bool ring_zero_copy = false;
-  float *d_scratch = nullptr;
-  int *d_gcount = nullptr;
-  size_t scratch_cap = 0, gcount_cap = 0;
+  SplitBuf host_split, dev_split;  // batch-host pipeline (h->stream) / batch-device launches (caller's stream)
   cudaStream_t stream = nullptr;     // streaming path + batch_host compute
   cudaStream_t copy_stream = nullptr;
   int64_t launches = 0;
@@ -213,48 +221,53 @@ int pick_split(const crn_handle *h, int64_t ngroups) {
   return best;
 }
 
-// Scratch rows and arrival counters for a split launch.  Growing them waits for the device: earlier launches of
-// this handle may still be using the old buffers.
-int ensure_split_buffers(crn_handle *h, int64_t ngroups, int split) {
+// Scratch rows and arrival counters for a split launch.  Growing them waits for the device: earlier launches that
+// own this buffer may still be using the old allocation.
+int ensure_split_buffers(const crn_handle *h, SplitBuf &b, int64_t ngroups, int split) {
   const size_t need_s = (size_t)ngroups * split * h->cfg.nsegs, need_c = (size_t)ngroups;
-  if (need_s <= h->scratch_cap && need_c <= h->gcount_cap) return CRN_OK;
+  if (need_s <= b.scratch_cap && need_c <= b.gcount_cap) return CRN_OK;
   CRN_CUDA(cudaDeviceSynchronize());
-  if (need_s > h->scratch_cap) {
-    cudaFree(h->d_scratch);
-    h->d_scratch = nullptr;
-    h->scratch_cap = 0;
-    CRN_CUDA(cudaMalloc(&h->d_scratch, sizeof(float) * need_s));
-    h->scratch_cap = need_s;
+  if (need_s > b.scratch_cap) {
+    cudaFree(b.d_scratch);
+    b.d_scratch = nullptr;
+    b.scratch_cap = 0;
+    CRN_CUDA(cudaMalloc(&b.d_scratch, sizeof(float) * need_s));
+    b.scratch_cap = need_s;
   }
-  if (need_c > h->gcount_cap) {
-    cudaFree(h->d_gcount);
-    h->d_gcount = nullptr;
-    h->gcount_cap = 0;
-    CRN_CUDA(cudaMalloc(&h->d_gcount, sizeof(int) * need_c));
-    CRN_CUDA(cudaMemset(h->d_gcount, 0, sizeof(int) * need_c));
-    h->gcount_cap = need_c;
+  if (need_c > b.gcount_cap) {
+    cudaFree(b.d_gcount);
+    b.d_gcount = nullptr;
+    b.gcount_cap = 0;
+    CRN_CUDA(cudaMalloc(&b.d_gcount, sizeof(int) * need_c));
+    CRN_CUDA(cudaMemset(b.d_gcount, 0, sizeof(int) * need_c));
+    b.gcount_cap = need_c;
   }
   return CRN_OK;
 }
+void free_split_buffers(SplitBuf &b) {
+  cudaFree(b.d_scratch);
+  cudaFree(b.d_gcount);
+  b = SplitBuf();
+}
 
 // Fills the launch-shape dependent fields of p (split, scratch) and returns the grid size through *grid.
-int shape_launch(crn_handle *h, crn::SenseParams &p, int64_t ngroups, int *grid) {
+int shape_launch(crn_handle *h, crn::SenseParams &p, int64_t ngroups, SplitBuf &buf, int *grid) {
   p.split = pick_split(h, ngroups);
   p.kp = h->cfg.navg / p.split;
   p.nwork = ngroups * p.split;
   p.scratch = nullptr;
   p.gcount = nullptr;
   if (p.split > 1) {
-    int st = ensure_split_buffers(h, ngroups, p.split);
+    int st = ensure_split_buffers(h, buf, ngroups, p.split);
     if (st != CRN_OK) return st;
-    p.scratch = h->d_scratch;
-    p.gcount = h->d_gcount;
+    p.scratch = buf.d_scratch;
+    p.gcount = buf.d_gcount;
   }
   *grid = grid_for(h, ngroups * p.split);
   return CRN_OK;
 }
 
-int launch(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat, double *d_ann,
+int launch(crn_handle *h, SplitBuf &split, const void *d_iq, int64_t ngroups, float *d_feat, double *d_ann,
            int32_t *d_dec, unsigned long long *d_mask, cudaStream_t s) {
   if (ngroups <= 0) return CRN_OK;
   crn::SenseParams p = h->base;
@@ -268,7 +281,7 @@ int launch(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat, doub
   p.use_tma = (p.upg == 0) && h->allow_tma && ((reinterpret_cast<uintptr_t>(d_iq) & 15) == 0) &&
               ((h->stride * h->sample_bytes) % 16 == 0) && ((h->cfg.frame_len * h->sample_bytes) % 16 == 0);
   int grid = 1;
-  int st = shape_launch(h, p, ngroups, &grid);
+  int st = shape_launch(h, p, ngroups, split, &grid);
   if (st != CRN_OK) return st;
   st = h->launch(p, h->cfg.window, h->cfg.detector, grid, s, nullptr);
   if (st == CRN_OK) h->launches++;
@@ -433,6 +446,7 @@ int crn_destroy(crn_handle *h) {
     cudaFreeHost(s.h_iq);
     cudaFree(s.d_iq);
     free_results(s.res);
+    free_split_buffers(s.split);
     if (s.done) cudaEventDestroy(s.done);
   }
   for (int i = 0; i < 2; i++) {
@@ -444,8 +458,8 @@ int crn_destroy(crn_handle *h) {
   }
   cudaFree(h->d_tw);
   cudaFree(h->d_win);
-  cudaFree(h->d_scratch);
-  cudaFree(h->d_gcount);
+  free_split_buffers(h->host_split);
+  free_split_buffers(h->dev_split);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -495,7 +509,7 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   CRN_CUDA(cudaHostGetDevicePointer((void **)&p.mask, s.res.h_mask, 0));
   p.ngroups = 1;
   int grid = 1;
-  int st = shape_launch(h, p, 1, &grid);  // one decision: its K frames are dealt to several CTAs
+  int st = shape_launch(h, p, 1, s.split, &grid);  // one decision: its K frames are dealt to several CTAs
   if (st != CRN_OK) return st;
   st = h->launch(p, h->cfg.window, h->cfg.detector, grid, h->stream, nullptr);
   if (st != CRN_OK) return st;
@@ -541,7 +555,7 @@ int crn_sense_batch_device(crn_handle *h, const void *d_iq, int64_t ngroups, flo
   if (!h || !d_iq || !d_feat || ngroups < 0)
     return crn::fail(CRN_ERR_INVALID, "crn_sense_batch_device: bad argument");
   CRN_CUDA(cudaSetDevice(h->device));
-  return launch(h, d_iq, ngroups, d_feat, d_ann, d_decision,
+  return launch(h, h->dev_split, d_iq, ngroups, d_feat, d_ann, d_decision,
                 (unsigned long long *)d_mask, (cudaStream_t)cuda_stream);
 }
 
@@ -601,7 +615,7 @@ int crn_sense_batch_host(crn_handle *h, const void *iq_, int64_t ngroups, crn_re
     CRN_CUDA(cudaEventRecord(h->stage_copied[b], h->copy_stream));
     CRN_CUDA(cudaStreamWaitEvent(h->stream, h->stage_copied[b], 0));
     ResultBuf &r = h->stage_res[b];
-    st = launch(h, h->d_stage[b], n, r.d_feat, r.d_ann, r.d_dec, r.d_mask, h->stream);
+    st = launch(h, h->host_split, h->d_stage[b], n, r.d_feat, r.d_ann, r.d_dec, r.d_mask, h->stream);
     if (st != CRN_OK) return st;
     st = fetch_results_async(r, n, h->cfg.nbands, h->stream);
     if (st != CRN_OK) return st;
