@@ -170,6 +170,12 @@ int crn_synth_config_default(crn_synth_config *sc, int32_t group_samples) {
   sc->hop_mode = 0;
   sc->dwell_groups = 64;
   sc->group_samples = group_samples;
+  sc->intf_type = CRN_INTF_NONE;
+  sc->intf_period_groups = 0;
+  sc->intf_offset_hz = 0.0;
+  sc->intf_rate = 1e6;      // scenarios/interferer defaults to tx_rate 1e6 in src/crts.cpp
+  sc->intf_gain_db = -3.0;  // interferer.cpp:32
+  sc->intf_duty = 1.0;      // interferer.cpp:29
   return CRN_OK;
 }
 

@@ -11,6 +11,10 @@
 //   - hopping: CE_PU_MARKOV_Chain_Tx.cpp:88-128 / CE_Random_Behaviour_PU.cpp:47-49, one draw per
 //     dwell; the chain itself is sequential and tiny, so it is walked on the host and uploaded.
 //   - complex AWGN at the stated in-band SNR (counter-hash Box-Muller).
+//   - optionally an interferer node (src/interferer.cpp): the waveforms that need no modem - CW (:128-134),
+//     uniform noise (:136-142), Gaussian noise exactly as coded, mean 5 / sigma 5 (:24,144-154) - generated at
+//     the interferer's own rate, held to the receiver rate, scaled by its soft gain (:32,189), mixed to its
+//     offset and gated by its duty cycle (:395-409).
 // The CPU statement of the same definition is oracle/crn_oracle.c:crn_oracle_synth (test infrastructure).
 #include <cuda_runtime.h>
 
@@ -56,6 +60,12 @@ struct SynthParams {
   int group_samples;
   float gain, sigc;
   double cyc_per_sample[3];
+  // interferer
+  int intf_type;
+  long long intf_period, intf_on;  // duty cycle in samples (period <= 0: always on)
+  double intf_rate_ratio;          // interferer samples per receiver sample
+  double intf_cyc_per_sample;
+  float intf_gain;
 };
 
 __device__ __forceinline__ void subcarrier(unsigned long long sseed, long long m, int k, float &re, float &im) {
@@ -127,6 +137,29 @@ __global__ void __launch_bounds__(256) synth_kernel(const SynthParams p) {
     sincosf(6.283185307179586f * u2, &ns, &nc);
     outr += rad * nc;
     outi += rad * ns;
+    if (p.intf_type != CRN_INTF_NONE && (p.intf_period <= 0 || (s % p.intf_period) < p.intf_on)) {
+      const unsigned long long im = (unsigned long long)((double)s * p.intf_rate_ratio);  // its sample index
+      float br2 = 0.5f, bi2 = 0.5f;  // CW
+      if (p.intf_type != CRN_INTF_CW) {
+        const unsigned long long hi = mix64(sseed ^ mix64(0x1F7E2A5C00000000ull + 2ull * im));
+        const float v1 = (float)(hi >> 40) * (1.0f / 16777216.0f), v2 = (float)((hi >> 16) & 0xFFFFFFull) * (1.0f / 16777216.0f);
+        if (p.intf_type == CRN_INTF_NOISE) {
+          br2 = 0.5f * v1 - 0.25f;
+          bi2 = 0.5f * v2 - 0.25f;
+        } else {  // independent N(5, 5) draws for the two components: the two Box-Muller outputs
+          const float r5 = 5.0f * sqrtf(-2.0f * logf((float)((hi >> 40) + 1ull) * (1.0f / 16777216.0f)));
+          float gs, gc;
+          sincosf(6.283185307179586f * v2, &gs, &gc);
+          br2 = 5.0f + r5 * gc;
+          bi2 = 5.0f + r5 * gs;
+        }
+      }
+      const double icyc = (double)s * p.intf_cyc_per_sample;
+      float jr, ji;
+      sincosf(6.283185307179586f * (float)(icyc - floor(icyc)), &ji, &jr);
+      outr += p.intf_gain * (br2 * jr - bi2 * ji);
+      outi += p.intf_gain * (br2 * ji + bi2 * jr);
+    }
     p.iq[i] = make_float2(outr, outi);
   }
 }
@@ -158,6 +191,12 @@ int synth_launch(const crn_synth_config *sc, int32_t device, void *d_iq, int64_t
   const double sigma2 = ps * sc->fs / (bocc * pow(10.0, sc->snr_db / 10.0));
   p.sigc = (float)sqrt(sigma2 / 2.0);
   for (int c = 0; c < 3; c++) p.cyc_per_sample[c] = sc->offsets_hz[c] / sc->fs;
+  p.intf_type = sc->intf_type;
+  p.intf_period = (long long)sc->intf_period_groups * sc->group_samples;
+  p.intf_on = (long long)llround(sc->intf_duty * (double)p.intf_period);
+  p.intf_rate_ratio = sc->intf_rate / sc->fs;
+  p.intf_cyc_per_sample = sc->intf_offset_hz / sc->fs;
+  p.intf_gain = (float)pow(10.0, sc->intf_gain_db / 20.0);
 
   // walk every stream's hop chain on the host from dwell 0 (sequential by definition) and upload it
   const long long ndwell = (first_sample + sps + p.dwell_samples - 1) / p.dwell_samples;
@@ -202,6 +241,9 @@ extern "C" int crn_synth_generate_device(const crn_synth_config *sc, int32_t dev
                                          void *cuda_stream) {
   if (!sc || !d_iq || first_sample < 0 || nsamples < 0 || sc->group_samples < 1 || sc->dwell_groups < 1)
     return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_device: bad argument");
+  if (sc->intf_type < CRN_INTF_NONE || sc->intf_type > CRN_INTF_AWGN ||
+      (sc->intf_type != CRN_INTF_NONE && (!(sc->intf_rate > 0.0) || sc->intf_duty < 0.0 || sc->intf_duty > 1.0)))
+    return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_device: bad interferer settings");
   if (d_state && ((first_sample % sc->group_samples) != 0 || (nsamples % sc->group_samples) != 0))
     return crn::fail(CRN_ERR_INVALID, "first_sample and nsamples must be group aligned when d_state is requested");
   return synth_launch(sc, device, d_iq, 0, 1, first_sample, nsamples, d_state, cuda_stream);
@@ -214,6 +256,9 @@ extern "C" int crn_synth_generate_streams_device(const crn_synth_config *sc, int
   if (!sc || !d_iq || first_stream < 0 || nstreams < 0 || samples_per_stream < 0 || sc->group_samples < 1 ||
       sc->dwell_groups < 1)
     return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_streams_device: bad argument");
+  if (sc->intf_type < CRN_INTF_NONE || sc->intf_type > CRN_INTF_AWGN ||
+      (sc->intf_type != CRN_INTF_NONE && (!(sc->intf_rate > 0.0) || sc->intf_duty < 0.0 || sc->intf_duty > 1.0)))
+    return crn::fail(CRN_ERR_INVALID, "crn_synth_generate_streams_device: bad interferer settings");
   if (d_state && (samples_per_stream % sc->group_samples) != 0)
     return crn::fail(CRN_ERR_INVALID, "samples_per_stream must be group aligned when d_state is requested");
   return synth_launch(sc, device, d_iq, first_stream, nstreams, 0, samples_per_stream, d_state, cuda_stream);

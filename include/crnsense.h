@@ -254,7 +254,21 @@ typedef struct crn_synth_config {
                            (CE_PU_MARKOV_Chain_Tx.cpp:97-128), 2: uniform (CE_Random_Behaviour_PU.cpp:47-49) */
   int32_t dwell_groups; /* decisions per PU dwell */
   int32_t group_samples;/* samples per decision group (K * frame_stride) */
+  /* Optional interferer node (src/interferer.cpp), added on top of the PU and the noise: */
+  int32_t intf_type;    /* enum crn_interferer: 0 none */
+  int32_t intf_period_groups; /* duty-cycle period in decision groups (its wall-clock `period`, interferer.cpp:28,
+                           395-409, scaled like the PU dwell); <= 0: always on */
+  int32_t reserved_;
+  double intf_offset_hz;/* interferer tx_freq - fc */
+  double intf_rate;     /* its sample rate (tx_rate); every generated sample is held for fs/intf_rate receiver samples */
+  double intf_gain_db;  /* soft gain (default -3 dB, interferer.cpp:32) plus whatever path loss is wanted */
+  double intf_duty;     /* on for duty*period, then off for (1-duty)*period (interferer.cpp:395-409) */
 } crn_synth_config;
+
+/* Interference waveforms of src/interferer.cpp that need no modem: CW = the constant 0.5+0.5j of
+   BuildCWTransmission (:128-134), NOISE = uniform in [-0.25, 0.25) per component (BuildNOISETransmission
+   :136-142), AWGN = Gaussian with MEAN 5 and sigma 5 per component, as coded (dist(5.0, 5.0) :24, :144-154). */
+enum crn_interferer { CRN_INTF_NONE = 0, CRN_INTF_CW = 1, CRN_INTF_NOISE = 2, CRN_INTF_AWGN = 3 };
 
 int crn_synth_config_default(crn_synth_config *sc, int32_t group_samples);
 

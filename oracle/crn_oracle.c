@@ -338,6 +338,34 @@ static void synth_range(const crn_synth_config *sc, uint64_t stream_seed, const 
     const float rad = sigc * sqrtf(-2.0f * logf(u1));
     outr += rad * cosf(6.283185307179586f * u2);
     outi += rad * sinf(6.283185307179586f * u2);
+    /* interferer node (src/interferer.cpp): CW :128-134, uniform noise :136-142, N(5,5) "AWGN" :24,144-154;
+       its own sample rate held to ours, soft gain :32,189, mixed to its offset, duty cycle :395-409 */
+    if (sc->intf_type != CRN_INTF_NONE) {
+      const int64_t period = (int64_t)sc->intf_period_groups * sc->group_samples;
+      const int64_t on = (int64_t)llround(sc->intf_duty * (double)period);
+      if (period <= 0 || (s % period) < on) {
+        const uint64_t im = (uint64_t)((double)s * (sc->intf_rate / sc->fs));
+        float br2 = 0.5f, bi2 = 0.5f;
+        if (sc->intf_type != CRN_INTF_CW) {
+          const uint64_t hi = mix64(stream_seed ^ mix64(0x1F7E2A5C00000000ull + 2ull * im));
+          const float v1 = (float)(hi >> 40) * (1.0f / 16777216.0f), v2 = (float)((hi >> 16) & 0xFFFFFF) * (1.0f / 16777216.0f);
+          if (sc->intf_type == CRN_INTF_NOISE) {
+            br2 = 0.5f * v1 - 0.25f;
+            bi2 = 0.5f * v2 - 0.25f;
+          } else {
+            const float r5 = 5.0f * sqrtf(-2.0f * logf((float)((hi >> 40) + 1) * (1.0f / 16777216.0f)));
+            br2 = 5.0f + r5 * cosf(6.283185307179586f * v2);
+            bi2 = 5.0f + r5 * sinf(6.283185307179586f * v2);
+          }
+        }
+        const double icyc = (double)s * (sc->intf_offset_hz / sc->fs);
+        const float iph = (float)(icyc - floor(icyc));
+        const float jr = cosf(6.283185307179586f * iph), ji = sinf(6.283185307179586f * iph);
+        const float ig = (float)pow(10.0, sc->intf_gain_db / 20.0);
+        outr += ig * (br2 * jr - bi2 * ji);
+        outi += ig * (br2 * ji + bi2 * jr);
+      }
+    }
     iq[2 * i] = outr;
     iq[2 * i + 1] = outi;
   }

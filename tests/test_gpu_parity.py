@@ -323,6 +323,19 @@ def test_synth_kernel_matches_cpu_statement(crn, oracle, torch):
         # same definition, float32 on both sides; libm vs CUDA sincos/log differ in the last ulps
         assert np.abs(got - want).max() <= 2e-4
         assert np.abs(got - want).mean() <= 5e-6
+    # interferer node on top (src/interferer.cpp waveforms that need no modem), duty-cycled
+    for itype, rate, scale in ((crn.INTF_CW, 1e6, 1.0), (crn.INTF_NOISE, 1e6, 1.0), (crn.INTF_AWGN, 2.5e6, 20.0)):
+        sci = crn.synth_config(gs, dwell_groups=2, snr_db=10.0, seed=12, hop_mode=0, intf_type=itype, intf_rate=rate,
+                               intf_offset_hz=-5.25e6, intf_period_groups=2, intf_duty=0.5)
+        crn.synth_generate(sci, d_iq, 0, n, None, 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        goti = d_iq.cpu().numpy().view(np.complex64).ravel()
+        wanti, _ = oracle.synth(sci, n)
+        assert np.abs(goti - wanti).max() <= 2e-4 * scale, itype
+        assert np.abs(wanti - want).max() > 0.1          # it is there
+    sc_bad = crn.synth_config(gs, intf_type=7)
+    with pytest.raises(crn.CrnError):
+        crn.synth_generate(sc_bad, d_iq, 0, n, None, 0, torch.cuda.current_stream().cuda_stream)
     # position independence (sharding): a window generated on its own equals the same window of the whole
     d_part = torch.empty(1000, 2, dtype=torch.float32, device="cuda")
     crn.synth_generate(sc, d_part, 2 * gs, 1000, None, 0, torch.cuda.current_stream().cuda_stream)

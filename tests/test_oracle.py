@@ -174,3 +174,41 @@ def test_synth_statistics(crn, oracle):
     # deterministic and position independent
     iq2, _ = oracle.synth(sc, 1000, first=gs + 17)
     assert np.array_equal(iq2, iq[gs + 17: gs + 1017])
+
+
+def test_synth_interferer_waveforms(crn, oracle):
+    """The interferer node's modem-free waveforms (src/interferer.cpp:128-154) on top of the PU capture: what is
+    added is exactly the documented waveform - checked by subtracting the interferer-free capture."""
+    gs = 4096
+    base_cfg = dict(dwell_groups=4, snr_db=10.0, seed=9)
+    clean, _ = oracle.synth(crn.synth_config(gs, **base_cfg), 8 * gs)
+    off, g = -5.2e6, 10 ** (-3.0 / 20.0)
+    n = np.arange(8 * gs)
+    carrier = np.exp(2j * np.pi * ((n * (off / 13e6)) % 1.0))
+    # CW: the constant 0.5 + 0.5j (BuildCWTransmission) at the interferer's offset, duty cycle 1/2 of 4 groups
+    sc = crn.synth_config(gs, intf_type=crn.INTF_CW, intf_offset_hz=off, intf_period_groups=4, intf_duty=0.5, **base_cfg)
+    d = oracle.synth(sc, 8 * gs)[0] - clean
+    on = ((n // gs) % 4) < 2
+    assert np.abs(d[~on]).max() == 0.0
+    assert np.abs(d[on] - (g * (0.5 + 0.5j) * carrier)[on]).max() <= 2e-5
+    # NOISE: uniform in [-0.25, 0.25) per component, one draw per interferer sample (1 MS/s held to 13 MS/s)
+    sc = crn.synth_config(gs, intf_type=crn.INTF_NOISE, intf_offset_hz=off, **base_cfg)
+    b = (oracle.synth(sc, 8 * gs)[0] - clean) / (g * carrier)
+    assert np.abs(b.real).max() <= 0.2501 and np.abs(b.imag).max() <= 0.2501
+    assert abs(b.real.mean()) < 0.01 and abs(b.real.var() - 0.25 / 12) < 0.003
+    held = (n * (1e6 / 13e6)).astype(np.int64)
+    same = held[1:] == held[:-1]
+    assert np.abs(b[1:][same] - b[:-1][same]).max() <= 2e-5 and np.abs(b[1:][~same] - b[:-1][~same]).mean() > 0.05
+    # AWGN as coded: normal_distribution(5.0, 5.0) per component -> a DC offset of 5 + 5j rides on the noise
+    sc = crn.synth_config(gs, intf_type=crn.INTF_AWGN, intf_offset_hz=off, intf_rate=13e6, **base_cfg)
+    b = (oracle.synth(sc, 8 * gs)[0] - clean) / (g * carrier)
+    assert abs(b.real.mean() - 5.0) < 0.15 and abs(b.imag.mean() - 5.0) < 0.15
+    assert abs(b.real.std() - 5.0) < 0.15 and abs(b.imag.std() - 5.0) < 0.15
+    # and the sensing path sees it: a CW in the noise-floor band (bins 300..309 of 512 = -5.38..-5.15 MHz) lifts NF^2
+    cfg = crn.config_reference()
+    cap = crn.synth_config(cfg.group_samples, dwell_groups=2, snr_db=10.0, seed=3)
+    jam = crn.synth_config(cfg.group_samples, dwell_groups=2, snr_db=10.0, seed=3, intf_type=crn.INTF_CW,
+                           intf_offset_hz=-5.25e6)
+    f0 = oracle.sense_port(cfg, oracle.synth(cap, 4 * cfg.group_samples)[0])[0]
+    f1 = oracle.sense_port(cfg, oracle.synth(jam, 4 * cfg.group_samples)[0])[0]
+    assert (f1[:, 0] > 50 * f0[:, 0]).all() and np.allclose(f1[:, 1:], f0[:, 1:], rtol=0.05)
