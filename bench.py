@@ -359,6 +359,10 @@ def run_ours(args):
     all_dec = cdist.gather_occupancy(d_dec)          # every rank sees the whole capture's decisions
     dec_hist = cdist.occupancy_histogram(d_dec)
     assert all_dec.numel() == world * ngroups
+    # cooperative fusion of the ranks' occupancy masks (8 B per decision over NCCL + one fusion kernel), also outside
+    fused = cdist.fuse_across_ranks(d_mask, max(cfg.nbands, 3), crn.FUSE_OR, stream)
+    torch.cuda.synchronize()
+    assert fused.numel() == ngroups and (world > 1 or torch.equal(fused, d_mask))
 
     # ---- end to end through the C-ABI host path: pinned host IQ -> H2D -> kernel -> D2H results --------
     e2e = None

@@ -48,3 +48,24 @@ def occupancy_histogram(decisions):
     if world()[0] > 1:
         dist.all_reduce(h, op=dist.ReduceOp.SUM)
     return h
+
+
+def fuse_across_ranks(masks, nbands, mode, stream=0):
+    """Cooperative sensing across GPUs (SURVEY 8f-4): every rank sensed the same time slots with its own radio;
+    the occupancy masks (uint64 per slot, CUDA tensor) are all-gathered over NCCL - 8 bytes per decision, the only
+    exchange there is - and fused on the device (OR / majority / AND, crn_fuse_masks_device).  Returns the fused
+    mask per slot, identical on every rank."""
+    import crn_b200 as crn
+    w, _ = world()
+    if not masks.is_cuda:
+        raise ValueError("fuse_across_ranks needs CUDA tensors: the fusion kernel has no CPU fallback")
+    masks = masks.contiguous()
+    if w == 1:
+        stack = masks.unsqueeze(0)
+    else:
+        parts = [torch.empty_like(masks) for _ in range(w)]
+        dist.all_gather(parts, masks)
+        stack = torch.stack(parts)
+    fused = torch.empty_like(masks)
+    crn.fuse_masks(stack.contiguous(), w, masks.numel(), nbands, mode, fused, masks.device.index or 0, stream)
+    return fused

@@ -557,6 +557,14 @@ def test_cooperative_fusion(crn, torch):
         assert np.array_equal(d_out.cpu().numpy().view(np.uint64), want)
     with pytest.raises(crn.CrnError):
         crn.fuse_masks(d_masks, 0, nslots, nbands, 0, d_out)
+    # the cross-rank wrapper (all-gather over NCCL + the same kernel); with one rank it is the identity
+    import importlib
+    cdist = importlib.import_module("crn_b200.dist")
+    one = cdist.fuse_across_ranks(d_masks[0], nbands, crn.FUSE_MAJORITY, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(one, d_masks[0])
+    with pytest.raises(ValueError):
+        cdist.fuse_across_ranks(d_masks[0].cpu(), nbands, crn.FUSE_OR)
 
 
 @pytest.mark.parametrize("nfft,navg", [(512, 10), (1024, 8), (4096, 4)])
