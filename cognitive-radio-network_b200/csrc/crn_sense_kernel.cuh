@@ -151,9 +151,15 @@ struct HybridPlan {
   // Measured with the packed-FP32 codelets (same binary, CRN_NO_TMA toggled): +5 % at N = 2048, +12 % at 4096,
   // +5 % at 8192 (Welch) / +14 % (64 sub-channels).
   static constexpr bool TMA = true;
-  // From N = 4096 the window table (16 / 32 KB) is what keeps one more CTA off the SM; there it is read
-  // through the read-only L1 path instead (the table is reused by every frame, L1 keeps it).
+  // The window table (8 / 16 / 32 KB) lives in shared memory.  With one frame per CTA the two large ones were what
+  // kept another CTA off the SM and were read through the read-only L1 path instead; with two frames per CTA
+  // (4096: 2 CTAs/SM, 8192: 1) they fit, and shared memory is the faster home: 4096 +2 % (reference bands) /
+  // +4 % (64 sub-channels), 8192 -1 % / +5 %.  -DCRN_WIN_L1 restores the L1 path from 4096 up (A/B).
+#ifdef CRN_WIN_L1
   static constexpr bool WIN_SMEM = (N < 4096);
+#else
+  static constexpr bool WIN_SMEM = true;
+#endif
   static constexpr bool PREFETCH = true;           // hybrid plans: +2 % (2048) ... +5 % (8192) with
   static_assert(C == 2 || C == 4 || C == 8, "hybrid plans cover N = 2048, 4096, 8192");
   static_assert(UNITS <= 15, "named barriers 1..15");
