@@ -49,6 +49,12 @@ struct RingSlot {
   unsigned char *d_iq = nullptr;  // device mirror
   ResultBuf res;
   SplitBuf split;
+  // device addresses of the pinned host buffers (zero-copy input / results), looked up once at create
+  const float2 *z_iq = nullptr;
+  float *z_feat = nullptr;
+  double *z_ann = nullptr;
+  int32_t *z_dec = nullptr;
+  unsigned long long *z_mask = nullptr;
   cudaEvent_t done = nullptr;
   uint64_t first_frame = 0;
   int state = 0;  // 0 free/filling, 1 in flight
@@ -430,6 +436,13 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     CRN_CUDA(cudaMalloc(&s.d_iq, slot_bytes));
     st = alloc_results(s.res, 1, cfg->nbands);
     if (st != CRN_OK) return st;
+    st = ensure_split_buffers(h, s.split, 1, h->max_split);  // now, not in front of the first decision
+    if (st != CRN_OK) return st;
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&s.z_iq, s.h_iq, 0));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&s.z_feat, s.res.h_feat, 0));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&s.z_ann, s.res.h_ann, 0));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&s.z_dec, s.res.h_dec, 0));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&s.z_mask, s.res.h_mask, 0));
     CRN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }
   guard.h = nullptr;
@@ -494,19 +507,17 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   if (h->ring_zero_copy) {
     // every sample is read exactly once, so the kernel can pull it across PCIe itself: transfer and FFTs overlap
     // frame by frame and there is no copy -> launch hand-over on the stream
-    void *dp = nullptr;
-    CRN_CUDA(cudaHostGetDevicePointer(&dp, s.h_iq, 0));
-    p.iq = reinterpret_cast<const float2 *>(dp);
+    p.iq = s.z_iq;
   } else {
     CRN_CUDA(cudaMemcpyAsync(s.d_iq, s.h_iq, slot_bytes, cudaMemcpyHostToDevice, h->stream));
     p.iq = reinterpret_cast<const float2 *>(s.d_iq);
   }
   // the decision's 52..300 bytes are written by the kernel straight into the slot's page-locked host mirror
   // (pinned memory is device-addressable): no device->host copies queue up behind the kernel
-  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.feat, s.res.h_feat, 0));
-  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.ann, s.res.h_ann, 0));
-  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.decision, s.res.h_dec, 0));
-  CRN_CUDA(cudaHostGetDevicePointer((void **)&p.mask, s.res.h_mask, 0));
+  p.feat = s.z_feat;
+  p.ann = s.z_ann;
+  p.decision = s.z_dec;
+  p.mask = s.z_mask;
   p.ngroups = 1;
   int grid = 1;
   int st = shape_launch(h, p, 1, s.split, &grid);  // one decision: its K frames are dealt to several CTAs
