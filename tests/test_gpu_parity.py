@@ -647,3 +647,62 @@ def test_streaming_decision_is_split_across_ctas(crn, oracle, torch):
     dec = np.array([r.decision for r in out], np.int32)
     check(crn, cfg, (feat, ann, dec, None), want)
     check(crn, cfg, again, want)
+
+
+def random_config(crn, rng):
+    """A random but valid sensing configuration: every knob of crn_config drawn independently."""
+    nfft = int(rng.choice([256, 512, 1024, 2048, 4096, 8192]))
+    cfg = crn.config_welch(max(nfft, 512), 4)
+    cfg.nfft = nfft
+    cfg.navg = int(rng.choice([1, 2, 3, 5, 8, 10, 16, 31, 32, 64]))
+    cfg.frame_len = int(rng.choice([nfft, nfft, nfft - 1, nfft // 2 + 3, 1 + rng.integers(0, nfft)]))
+    cfg.frame_stride = int(rng.choice([0, 0, cfg.frame_len + int(rng.integers(0, 19))]))
+    cfg.window = int(rng.integers(0, 2))
+    cfg.detector = int(rng.integers(0, 2))
+    cfg.postop = int(rng.integers(0, 3))
+    cfg.iq_format = int(rng.integers(0, 2))
+    cfg.decide = int(rng.integers(0, 3))
+    nbands = int(rng.integers(4, 65)) if cfg.decide == crn.DECIDE_ANN else int(rng.integers(1, 65))
+    cfg.nbands = nbands
+    # every band gets at least one segment; extra segments land on random bands (multi-segment bands,
+    # overlapping ranges and single-bin ranges all occur)
+    nsegs = int(min(128, nbands + rng.integers(0, 1 + min(64, 128 - nbands))))
+    bands = list(range(nbands)) + [int(b) for b in rng.integers(0, nbands, nsegs - nbands)]
+    for i, b in enumerate(bands):
+        lo = int(rng.integers(0, nfft))
+        hi = int(min(nfft, lo + 1 + rng.integers(0, max(1, nfft // 8))))
+        cfg.segs[i].band, cfg.segs[i].lo, cfg.segs[i].hi = b, lo, hi
+    cfg.nsegs = nsegs
+    cfg.energy_factor = float(rng.uniform(1.5, 6.0))
+    return cfg
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_configurations(crn, oracle, torch, seed):
+    """Seeded sweep over the whole configuration space against the CPU statement of the engine."""
+    rng = np.random.default_rng(1000 + seed)
+    cfg = random_config(crn, rng)
+    assert crn.validate(cfg) == crn.OK
+    ngroups = int(rng.integers(1, 8))
+    gs = cfg.group_samples
+    sc = crn.synth_config(gs, dwell_groups=1, snr_db=float(rng.choice([-5.0, 0.0, 10.0, 20.0])), seed=seed)
+    iq, _ = oracle.synth(sc, ngroups * gs)
+    if cfg.iq_format == crn.IQ_SC16:
+        iq = np.clip(np.round(iq.view(np.float32) * 32768.0), -32768, 32767).astype(np.int16)
+        want = oracle.sense_port(cfg, iq)
+        with crn.Sensor(cfg, device=0) as s:
+            got = s.sense_host(iq, ngroups)
+    else:
+        want = oracle.sense_port(cfg, iq)
+        got = run_device(crn, torch, cfg, iq)
+    if cfg.postop == crn.POST_SUM_DB:
+        # dB features: <= 1e-3 dB (BASELINE); bands that hold only rounding noise have no significant digits
+        f, of = got[0], want[0]
+        sig = of > of.max(axis=1, keepdims=True) - 70.0
+        assert np.abs(f - of)[sig].max() <= 1e-3
+        lin = (10.0 ** (f / 10.0), got[1], got[2], got[3])
+        olin = (10.0 ** (of / 10.0), want[1], want[2], want[3])
+        if cfg.decide == crn.DECIDE_ENERGY:
+            check(crn, cfg, lin, olin, realistic=False)
+    else:
+        check(crn, cfg, got, want, realistic=False)
