@@ -208,7 +208,11 @@ def cpu_leg(crn, cfg, iq_host, budget_s, threads=None):
     n = int(min(have, max(probe, rate * budget_s // gs)))
     passes = max(1, int(round(budget_s / (n * gs / rate))))
     secs = sum(oracle.time_port(cfg, iq_host[: n * gs * eps], n, nthreads) for _ in range(passes))
+    # the reference engine is single-threaded per radio: one thread on ~1 s of the same work
+    n1 = int(max(1, min(have, rate / max(nthreads, 1) // gs)))
+    t1 = oracle.time_port(cfg, iq_host[: n1 * gs * eps], n1, 1)
     return {"value": passes * n * gs / secs / 1e9, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "single_thread_value": n1 * gs / max(t1, 1e-9) / 1e9,
             "sample": "%d pass(es) over the first %d of %d decision groups (%d samples per pass) of the same synthetic "
                       "capture, %.1f s of CPU work on %d threads; reference algorithm restated in C (oracle/crn_oracle.c, "
                       "liquid-style radix-2 fp32 FFT; liquid-dsp/FFTW unavailable), one engine state per thread, gcc -O2"
