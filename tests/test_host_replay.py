@@ -211,3 +211,35 @@ def test_engine_follows_a_weight_file(crn, replay, tmp_path):
             assert np.array_equal(dec, g["decision"])
         else:
             assert not np.array_equal(dec, g["decision"])
+
+
+def test_registration_generator_scans_like_upstream(replay, tmp_path):
+    """host/src/config_cognitive_engines.cpp: CE_* directories holding CE_X.hpp + CE_X.cpp register, extra sources of
+    an engine directory ride along (src/config_cognitive_engines.cpp:82-107), anything else is ignored; --skip drops
+    an engine and the first directory that provides a name wins."""
+    gen = os.path.join(HOST, "config_cognitive_engines")
+    assert os.path.exists(gen)                      # built by the Makefile before the radio, like upstream's tool
+    a, b = tmp_path / "engines_a", tmp_path / "engines_b"
+    for d, names in ((a, ["CE_Alpha", "CE_Beta"]), (b, ["CE_Alpha", "CE_Gamma"])):
+        for n in names:
+            (d / n).mkdir(parents=True)
+            (d / n / (n + ".hpp")).write_text("// %s\n" % n)
+            (d / n / (n + ".cpp")).write_text("// %s\n" % n)
+    (a / "CE_Alpha" / "helper.c").write_text("\n")
+    (a / "CE_Alpha" / "notes.txt").write_text("\n")
+    (a / "CE_NoHeader").mkdir()
+    (a / "CE_NoHeader" / "CE_NoHeader.cpp").write_text("\n")
+    (a / "README").write_text("\n")
+    out = tmp_path / "lib"
+    r = subprocess.run([gen, "--engines", str(a), str(b), "--out", str(out), "--skip", "CE_Beta"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "registered 2 cognitive engine(s): CE_Alpha, CE_Gamma" in r.stdout
+    reg = (out / "ce_registry_generated.cpp").read_text()
+    assert reg.count("CRN_REGISTER_CE(") == 2 and "CRN_REGISTER_CE(CE_Alpha)" in reg and "CRN_REGISTER_CE(CE_Gamma)" in reg
+    assert str(a / "CE_Alpha" / "CE_Alpha.hpp") in reg and str(b / "CE_Alpha") not in reg
+    assert "crn_ce_registry_size() { return 2; }" in reg
+    mk = (out / "ce_engines.mk").read_text()
+    srcs = [l for l in mk.splitlines() if l.startswith("CE_SRCS")][0].split()[2:]
+    assert srcs == [str(a / "CE_Alpha" / "CE_Alpha.cpp"), str(a / "CE_Alpha" / "helper.c"),
+                    str(b / "CE_Gamma" / "CE_Gamma.cpp")]
+    assert subprocess.run([gen, "--bogus"], capture_output=True).returncode == 2
