@@ -1,4 +1,6 @@
-import sys; sys.path[:0]=['/root/repo','/root/repo/oracle','/root/repo/tests']
+"""Run-to-run determinism and sampled parity at scale (GPU box; not collected by pytest: python tests/stress_gpu.py).
+Lives under tests/ because it uses the oracle as its checker."""
+import sys; import os; _R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_R, os.path.join(_R, 'oracle'), os.path.join(_R, 'tests')]
 import numpy as np, torch, crn_b200 as crn, oracle
 torch.cuda.set_device(0)
 stream = torch.cuda.current_stream().cuda_stream
