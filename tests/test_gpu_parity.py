@@ -706,3 +706,29 @@ def test_random_configurations(crn, oracle, torch, seed):
             check(crn, cfg, lin, olin, realistic=False)
     else:
         check(crn, cfg, got, want, realistic=False)
+
+
+@pytest.mark.parametrize("force", [None, "0", "1"])
+def test_streaming_large_slots_read_in_place(crn, oracle, torch, monkeypatch, force):
+    """From 2 MiB per decision the kernel reads the pinned ring slot over PCIe itself (no host->device copy);
+    CRN_RING_COPY forces either way.  Same results as the CPU statement either way, slot after slot."""
+    if force is not None:
+        monkeypatch.setenv("CRN_RING_COPY", force)
+    cfg = crn.config_wideband(4096, 64, 64)          # 64 frames x 4096 samples x 8 B = 2 MiB per decision
+    cfg.ring_slots = 2
+    nd = 5
+    iq, _ = oracle.synth(crn.synth_config(cfg.group_samples, dwell_groups=1, snr_db=10.0, seed=77), nd * cfg.group_samples)
+    want = oracle.sense_port(cfg, iq)
+    frames = iq.reshape(-1, cfg.frame_len)
+    out = []
+    with crn.Sensor(cfg, device=0) as s:
+        for i, fr in enumerate(frames):
+            s.push_frame(fr)
+            if (i + 1) % cfg.navg == 0:
+                out.append(s.wait())
+    feat = np.array([[r.feat[b] for b in range(cfg.nbands)] for r in out], np.float32)
+    mask = np.array([r.occupancy_mask for r in out], np.uint64)
+    ann = np.zeros((nd, 3))
+    dec = np.zeros(nd, np.int32)
+    check(crn, cfg, (feat, ann, dec, mask), want)
+    assert [r.first_frame for r in out] == [cfg.navg * i for i in range(nd)]
