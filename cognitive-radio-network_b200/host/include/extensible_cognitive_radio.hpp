@@ -30,6 +30,7 @@
 #include <sys/time.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <complex>
 #include <fstream>
 #include <iostream>
@@ -123,11 +124,15 @@ public:
 private:
   CognitiveEngine *CE;
   double ce_timeout_ms;
-  int ce_sensing_flag;
+  // flags the workers read outside their mutexes (upstream uses plain ints / bools for these, e.g. the unlocked
+  // read of ce_sensing_flag at src/extensible_cognitive_radio.cpp:1310): atomics here, so the replay runtime is
+  // free of data races by construction
+  std::atomic<int> ce_sensing_flag;
   pthread_t CE_process, rx_process;
   pthread_mutex_t CE_mutex, rx_params_mutex, tx_params_mutex;
   pthread_cond_t CE_cond, CE_execute_sig, rx_cond, consumed_sig, done_sig;
-  bool ce_thread_running, ce_running, rx_thread_running, rx_running, capture_done;
+  std::atomic<bool> ce_thread_running, ce_running, rx_thread_running, rx_running;
+  bool capture_done;
   bool lockstep_, handoff_pending_;
   bool ce_ever_started_;  // lock-step replay: the rx worker holds the first packet until start_ce() has been called
   IqSource *src_;

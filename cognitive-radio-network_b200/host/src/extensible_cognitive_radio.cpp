@@ -95,7 +95,7 @@ void ExtensibleCognitiveRadio::stop_ce() {
 }
 void ExtensibleCognitiveRadio::set_ce_timeout_ms(double t) { ce_timeout_ms = t; }
 double ExtensibleCognitiveRadio::get_ce_timeout_ms() { return ce_timeout_ms; }
-void ExtensibleCognitiveRadio::set_ce_sensing(int on) { ce_sensing_flag = on; }  // plain int upstream too
+void ExtensibleCognitiveRadio::set_ce_sensing(int on) { ce_sensing_flag = on; }  // no lock, as upstream (cpp:389-391)
 
 #define LOCKED(m, stmt)        \
   do {                         \
