@@ -49,21 +49,24 @@ WORKLOADS = {
     # name: (description, builder(crn) -> (cfg, ngroups, streams))
     "config2": WORKLOAD,
     "wideband": "configs[2]: wideband sweep, 8192-pt FFT, 64 equal sub-channels, 100 MHz equivalent rate, energy-detection features, 64-frame average, 1e9 complex-float samples",
-    "multiradio": "configs[3]: multi-radio, 4096 independent sensing streams (simulated CORNET nodes), 2048-pt FFT, 64-frame Welch average + ANN, one decision per stream (537e6 samples)",
+    "multiradio": "configs[3]: multi-radio, 4096 independent sensing streams (simulated CORNET nodes), 2048-pt FFT, 64-frame Welch average + ANN, one decision per stream (537e6 samples), streams sharded over the GPUs by stream id (strong scaling)",
+    "multiradio_weak": "configs[3] shape, weak scaling: every GPU its own 4096 sensing streams, 2048-pt FFT, 64-frame Welch average + ANN",
     "sc16": "configs[1] fed in the USRP wire format: 1024-pt FFT, Hann, 64-frame Welch average + ANN, 1e9 samples as int16 (I,Q) pairs (4 B/sample), converted on the GPU",
     "refexact": "configs[0] on the GPU: reference-exact mode, 512-pt FFT, no window, |X| averaged over 10 frames, (sum)^2 features + ANN, 1e9 complex-float samples",
 }
 ACTIVE = {"name": "config2"}
 
 
-def workload_config(crn):
+def workload_config(crn, name=None):
     """Returns (cfg, decision groups per GPU).  The default - and the only bench line the contract asks for -
-    is BASELINE configs[1]; the others are the remaining BASELINE configs, selectable with --workload."""
-    w = ACTIVE["name"]
+    is BASELINE configs[1]; the others are the remaining BASELINE configs, selectable with --workload.
+    `crn` is whoever supplies the config structs: the product's ctypes mirror (our arm) or the oracle's own
+    (reference arm, which must not load the product library); both offer the same four constructors."""
+    w = name or ACTIVE["name"]
     if w == "wideband":
         cfg = crn.config_wideband(8192, 64, 64)
         return cfg, TOTAL_SAMPLES // cfg.group_samples
-    if w == "multiradio":
+    if w in ("multiradio", "multiradio_weak"):
         cfg = crn.config_welch(2048, 64)
         return cfg, 4096
     if w == "refexact":
@@ -71,7 +74,7 @@ def workload_config(crn):
         return cfg, TOTAL_SAMPLES // cfg.group_samples
     cfg = crn.config_welch(NFFT, NAVG)
     if w == "sc16":
-        cfg.iq_format = crn.IQ_SC16
+        cfg.iq_format = 1  # CRN_IQ_SC16
     return cfg, TOTAL_SAMPLES // cfg.group_samples  # 15258 full decisions, remainder dropped
 
 
@@ -183,17 +186,6 @@ def measured_peak():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def profiled_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
-
-
 def cpu_leg(crn, cfg, iq_host, budget_s, threads=None):
     """Oracle port on the host cores on a bounded sample of the same IQ: about `budget_s` seconds of
     all-core work (whole passes over the first groups of the capture).  Returns the cpu_baseline dict."""
@@ -221,17 +213,18 @@ def cpu_leg(crn, cfg, iq_host, budget_s, threads=None):
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path on the host cores (no GPU code on this path)."""
+    """The reference's own CPU implementation of the path on the host cores.  Nothing of the product is on this path:
+    the workload comes from the oracle's own config statement (oracle/crn_oracle_config.c) and libcrnsense.so is
+    never loaded into this process (checked below)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
-    import crn_b200 as crn  # config structs only
     oracle = _oracle()
-    cfg, ngroups = workload_config(crn)
+    cfg, ngroups = workload_config(oracle)
     gs = cfg.group_samples
     nthreads = oracle.port().crn_oracle_max_threads()
-    sc = synth_cfg(crn, cfg)
+    sc = synth_cfg(oracle, cfg)
     # bounded sample per step: ~budget seconds of all-core CPU work, whole run within a few minutes
     total_steps = args.steps + args.warmup
     budget = min(4.0, max(0.25, 150.0 / max(total_steps, 1)))
@@ -241,14 +234,25 @@ def run_reference(args):
     n = int(max(probe_groups, min(2048, (probe_groups * budget / max(t, 1e-9)))))
     if n > probe_groups:
         iq, _ = oracle.synth(sc, n * gs)
-    for _ in range(args.warmup):
-        oracle.time_port(cfg, iq, n, nthreads)
-    secs = [oracle.time_port(cfg, iq, n, nthreads) for _ in range(args.steps)]
-    tot = sum(secs)
+    # two builds of the same C statement: -O2 (what the tests check against) and -O3 -march=native built on this
+    # host; the line reports the faster one
+    builds = [("gcc -O2", None)]
+    if oracle.native() is not None:
+        builds.append(("gcc -O3 -march=native (built on this host)", oracle.native()))
+    runs = {}
+    for name, lib in builds:
+        for _ in range(args.warmup):
+            oracle.time_port(cfg, iq, n, nthreads, lib)
+        runs[name] = sum(oracle.time_port(cfg, iq, n, nthreads, lib) for _ in range(args.steps))
+    best = min(runs, key=runs.get)
+    tot = runs[best]
     value = args.steps * n * gs / tot / 1e9
     sample = ("each step = first %d decision groups (%d samples) of the synthetic capture, all %d host threads, "
               "reference algorithm restated in C with this workload's options (the unmodified engine is fixed at "
-              "N=512/K=10/no window and cannot express it)" % (n, n * gs, nthreads))
+              "N=512/K=10/no window and cannot express it); liquid-style radix-2 fp32 FFT (liquid-dsp absent; FFTW3f %s "
+              "on this host); reported build: %s; all builds: %s"
+              % (n, n * gs, nthreads, "installed but unused" if oracle.fftw_installed() else "not installed", best,
+                 ", ".join("%s %.3f GS/s" % (k, args.steps * n * gs / v / 1e9) for k, v in runs.items())))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -258,54 +262,67 @@ def run_reference(args):
             "gpu_launches": 0}
     # the unmodified reference engine in its own (only) mode, for context
     if oracle.ref() is not None:
-        rcfg = crn.config_reference()
-        rsc = crn.synth_config(rcfg.group_samples, dwell_groups=64, snr_db=10.0, seed=12)
+        rcfg = oracle.config_reference()
+        rsc = oracle.synth_config(rcfg.group_samples, dwell_groups=64, snr_db=10.0, seed=12)
         rn = nthreads * 2000
         riq, _ = oracle.synth(rsc, rn * rcfg.group_samples)
         sec, nd = oracle.time_ref(riq, 512, rn * 10, nthreads)
         line["reference_engine_native_mode"] = {
             "value": rn * rcfg.group_samples / sec / 1e9, "unit": UNIT, "cores": nthreads, "kind": "reference",
             "sample": "unmodified CE_Predictive_Node.cpp (oracle/_ref), N=512 K=10 rect |X|, %d decisions, one engine per thread" % nd}
+    with open("/proc/self/maps") as fh:
+        mapped = sorted({ln.split()[-1] for ln in fh if ln.rstrip().endswith(".so") and ROOT in ln})
+    line["native_so_mapped"] = [os.path.relpath(m, ROOT) for m in mapped]
+    assert not any("libcrnsense" in m for m in mapped), "the reference arm must not load the product library"
     print(json.dumps(line), flush=True)
     return 0
 
 
-def run_ours(args):
+def kernel_traffic(kernel_name):
+    """dram bytes per launch of this kernel from the committed ncu --set full captures (profiles/traffic.json is
+    keyed by kernel name: a capture of one kernel says nothing about another), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get("kernels", {}).get(kernel_name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class Ctx:
+    """What every measurement of this process shares: ranks, device, peak."""
+    pass
+
+
+def measure(ctx, name, steps, warmup, env=None, keep=False, parity_groups=64):
+    """Device-resident timing of ONE workload on this rank's GPU (+ parity spot check against the oracle, outside the
+    timed region).  A step = one fused launch over the rank's batch + the device->host read of its results
+    (features, MLP outputs, decisions, masks) into pinned memory: `first kernel launch to last feature readback`,
+    SURVEY 8d.  Returns a dict; with keep=True the tensors stay alive in it for the e2e leg."""
     import numpy as np
     import torch
-    import torch.distributed as dist
-    import crn_b200 as crn
-    import importlib
-    cdist = importlib.import_module("crn_b200.dist")
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; libcrnsense has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    cfg, ngroups = workload_config(crn)
+    crn, cdist, world, rank, local_rank, dev = ctx.crn, ctx.cdist, ctx.world, ctx.rank, ctx.local_rank, ctx.dev
+    cfg, ngroups_all = workload_config(crn, name)
+    strong = (name == "multiradio")
+    first, ngroups = (cdist.shard_groups(ngroups_all, world, rank) if strong else (rank * ngroups_all, ngroups_all))
     gs = cfg.group_samples
     nsamp = ngroups * gs
     stream = torch.cuda.current_stream().cuda_stream
-    sensor = crn.Sensor(cfg, device=local_rank)
+    saved = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        sensor = crn.Sensor(cfg, device=local_rank)   # CRN_* development switches are read once, at create
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     info = sensor.kernel_info()
-
-    # ---- synthetic capture, generated in HBM (rank r owns samples [r*nsamp, (r+1)*nsamp)) -------------
     d_iq = torch.empty(nsamp, 2, dtype=torch.float32, device=dev)
     d_state = torch.empty(ngroups, dtype=torch.int32, device=dev)
-    if ACTIVE["name"] == "multiradio":   # rank r owns streams [r*ngroups, (r+1)*ngroups), one group each
-        crn.synth_generate_streams(synth_cfg(crn, cfg), d_iq, rank * ngroups, ngroups, gs, d_state, local_rank, stream)
-    else:
+    if name in ("multiradio", "multiradio_weak"):   # one decision group per stream; this rank's streams by stream id
+        crn.synth_generate_streams(synth_cfg(crn, cfg), d_iq, first, ngroups, gs, d_state, local_rank, stream)
+    else:                                            # rank r owns samples [r*nsamp, (r+1)*nsamp) of one long capture
         crn.synth_generate(synth_cfg(crn, cfg), d_iq, rank * nsamp, nsamp, d_state, local_rank, stream)
     sample_bytes = 8
     if cfg.iq_format == crn.IQ_SC16:   # quantise the capture to the 16-bit wire format, in place chunks
@@ -320,56 +337,135 @@ def run_ours(args):
     d_ann = torch.empty(ngroups, 3, dtype=torch.float64, device=dev)
     d_dec = torch.empty(ngroups, dtype=torch.int32, device=dev)
     d_mask = torch.empty(ngroups, dtype=torch.int64, device=dev)
+    h_res = [torch.empty_like(t, device="cpu").pin_memory() for t in (d_feat, d_ann, d_dec, d_mask)]
+    d2h_bytes = sum(t.numel() * t.element_size() for t in h_res)
 
     def step():
         sensor.sense_device(d_iq, ngroups, d_feat, d_ann, d_dec, d_mask, stream)
 
-    for _ in range(max(args.warmup, 3)):
+    def readback():
+        for h, d in zip(h_res, (d_feat, d_ann, d_dec, d_mask)):
+            h.copy_(d, non_blocking=True)
+
+    for _ in range(max(warmup, 3)):
         step()
-    barrier()
+        readback()
+    ctx.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.25 if keep else 0.05)
     launches0 = sensor.launches
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    ctx.barrier()
     t_wall0 = time.time()
     ev[0].record()
-    for i in range(args.steps):
+    for i in range(steps):
         step()
-        ev[i + 1].record()
-    barrier()
+        ev[2 * i + 1].record()      # kernel done (roofline: launch duration)
+        readback()
+        ev[2 * i + 2].record()      # results in pinned host memory (value: to last feature readback)
+    ctx.barrier()
     t_wall1 = time.time()
     gpu_launches = sensor.launches - launches0
-    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    kern_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)]
     total_ms = ev[0].elapsed_time(ev[-1])
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     total_ms_max = cdist.max_over_ranks(total_ms, dev)
-    value = world * nsamp * args.steps / (total_ms_max * 1e-3) / 1e9
+    total_samples = (ngroups_all * gs) if strong else world * nsamp
+    value = total_samples * steps / (total_ms_max * 1e-3) / 1e9
 
     # ---- parity spot check of this very batch against the oracle (outside every timed region) ----------
-    pick = sorted(set([0, ngroups // 2, ngroups - 1]))
-    if cfg.iq_format == crn.IQ_SC16:
-        iq_pick = np.concatenate([d_iq[g * gs:(g + 1) * gs].cpu().numpy().ravel() for g in pick])
-    else:
-        iq_pick = np.concatenate([d_iq[g * gs:(g + 1) * gs].cpu().numpy().view(np.complex64).ravel() for g in pick])
+    pick = sorted(set(int(round(i * (ngroups - 1) / max(parity_groups - 1, 1))) for i in range(min(parity_groups, ngroups))))
+    idx = torch.tensor(pick, device=dev)
+    rows = d_iq.view(ngroups, gs, 2)[idx].cpu().numpy()
+    iq_pick = rows.ravel() if cfg.iq_format == crn.IQ_SC16 else rows.view(np.complex64).ravel()
     oracle = _oracle()
-    of, oa, od, _ = oracle.sense_port(cfg, iq_pick)
-    gf, ga, gd = d_feat.cpu().numpy()[pick], d_ann.cpu().numpy()[pick], d_dec.cpu().numpy()[pick]
-    parity = {"groups": pick, "feat_max_rel": float((abs(gf - of) / abs(of)).max()),
-              "ann_max_abs": float(abs(ga - oa).max()), "decisions_equal": bool((gd == od).all())}
+    of, oa, od, om = oracle.sense_port(cfg, iq_pick, nthreads=oracle.port().crn_oracle_max_threads())
+    gf, ga, gd = h_res[0].numpy()[pick], h_res[1].numpy()[pick], h_res[2].numpy()[pick]
+    gm = h_res[3].numpy()[pick].astype(np.uint64)
+    parity = {"groups_checked": len(pick), "of_groups": ngroups,
+              "feat_max_rel": float((abs(gf - of) / abs(of)).max()),
+              "ann_max_abs": float(abs(ga - oa).max()), "decisions_equal": bool((gd == od).all()),
+              "masks_equal": bool((gm == om).all()),
+              "checker": "oracle/crn_oracle.c on the same IQ, groups spread evenly over the rank's batch; no tolerance floor"}
+    peak, peak_src = ctx.peak
+    kernel_ms = sum(kern_ms) / len(kern_ms)
+    achieved = nsamp * sample_bytes / (kernel_ms * 1e-3) / 1e9
+    out = {"name": name, "workload": WORKLOADS[name], "value": value, "ms_per_step": total_ms_max / steps,
+           "scaling": "strong" if strong else "weak", "steps": steps, "gpu_launches": int(gpu_launches),
+           "kernel": info["name"], "kernel_ms": kernel_ms, "kernel_ms_minmax": [min(kern_ms), max(kern_ms)],
+           "achieved_gbs": achieved, "frac": achieved / peak, "samples_per_gpu": nsamp, "groups_per_gpu": ngroups,
+           "total_samples": total_samples, "sample_bytes": sample_bytes, "d2h_bytes_per_step": d2h_bytes,
+           "parity_check": parity, "clocks": clocks, "kernel_info": info, "nfft": cfg.nfft, "navg": cfg.navg,
+           "nbands": cfg.nbands, "peak": peak, "peak_source": peak_src}
+    if env:
+        out["env"] = env
+    if keep:
+        out["_keep"] = dict(cfg=cfg, sensor=sensor, d_iq=d_iq, d_feat=d_feat, d_ann=d_ann, d_dec=d_dec, d_mask=d_mask,
+                            ngroups=ngroups, nsamp=nsamp, gs=gs, stream=stream)
+    else:
+        sensor.close()
+        del d_iq, d_feat, d_ann, d_dec, d_mask, d_state
+        torch.cuda.empty_cache()
+    return out
+
+
+# the other BASELINE configs, measured after the headline workload (5 steps each, own captures, outside its timed
+# region) so that the driver-run line carries them too: name -> (workload, environment switches read at crn_create)
+OTHER_WORKLOADS = {
+    "configs[0] reference-exact on the GPU": ("refexact", None),
+    "configs[1] with every bin live (no band-plan pruning)": ("config2", {"CRN_NO_PRUNE": "1"}),
+    "configs[2] wideband 8192-pt x 64 sub-channels": ("wideband", None),
+    "configs[3] multi-radio 4096 streams x 2048-pt, sharded by stream id": ("multiradio", None),
+}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import crn_b200 as crn
+    import importlib
+    cdist = importlib.import_module("crn_b200.dist")
+
+    ctx = Ctx()
+    ctx.crn, ctx.cdist = crn, cdist
+    world = ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = ctx.rank = int(os.environ.get("RANK", "0"))
+    local_rank = ctx.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libcrnsense has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = ctx.dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ctx.barrier = barrier
+    ctx.peak = measured_peak()
+
+    main = measure(ctx, ACTIVE["name"], args.steps, args.warmup, keep=True)
+    k = main.pop("_keep")
+    cfg, sensor, d_iq, d_feat, d_dec, d_mask = k["cfg"], k["sensor"], k["d_iq"], k["d_feat"], k["d_dec"], k["d_mask"]
+    ngroups, nsamp, stream = k["ngroups"], k["nsamp"], k["stream"]
+    sample_bytes = main["sample_bytes"]
+
     # optional occupancy exchange (north_star): outside the data path and the timed region
-    all_dec = cdist.gather_occupancy(d_dec)          # every rank sees the whole capture's decisions
+    counts = [cdist.shard_groups(4096, world, r)[1] for r in range(world)] if main["scaling"] == "strong" else None
+    all_dec = cdist.gather_occupancy(d_dec, counts)  # every rank sees the whole capture's decisions
     dec_hist = cdist.occupancy_histogram(d_dec)
-    assert all_dec.numel() == world * ngroups
+    assert all_dec.numel() == (sum(counts) if counts else world * ngroups)
     # cooperative fusion of the ranks' occupancy masks (8 B per decision over NCCL + one fusion kernel), also outside
-    fused = cdist.fuse_across_ranks(d_mask, max(cfg.nbands, 3), crn.FUSE_OR, stream)
-    torch.cuda.synchronize()
-    assert fused.numel() == ngroups and (world > 1 or torch.equal(fused, d_mask))
+    if counts is None or len(set(counts)) == 1:
+        fused = cdist.fuse_across_ranks(d_mask, max(cfg.nbands, 3), crn.FUSE_OR, stream)
+        torch.cuda.synchronize()
+        assert fused.numel() == ngroups and (world > 1 or torch.equal(fused, d_mask))
 
     # ---- end to end through the C-ABI host path: pinned host IQ -> H2D -> kernel -> D2H results --------
-    e2e = None
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h_iq = torch.empty(nsamp, 2, dtype=d_iq.dtype, pin_memory=True)
     h_iq.copy_(d_iq)
@@ -387,37 +483,54 @@ def run_ours(args):
     hf, ha, hd, _ = crn.results_to_arrays(res, cfg.nbands)
     # the host path launches 128-group chunks whose groups are split over several CTAs: equal to fp32 rounding
     e2e_ok = bool(np.allclose(hf, d_feat.cpu().numpy(), rtol=2e-6, atol=0) and np.array_equal(hd, d_dec.cpu().numpy()))
-    e2e = {"value": world * nsamp * e2e_steps / e2e_sec / 1e9, "unit": UNIT,
+    e2e = {"value": main["total_samples"] * e2e_steps / e2e_sec / 1e9, "unit": UNIT,
            "h2d_bytes_per_step": nsamp * sample_bytes, "d2h_bytes_per_step": ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8),
            "steps": e2e_steps, "path": "crn_sense_batch_host (C-ABI), pinned host IQ, 64 MiB double-buffered chunks; wall clock, max over ranks",
            "matches_device_path": e2e_ok}
+
+    # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same capture -----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        iq_host = h_iq.numpy().ravel() if cfg.iq_format == crn.IQ_SC16 else h_iq.numpy().view(np.complex64).ravel()
+        cpu = cpu_leg(crn, cfg, iq_host, args.cpu_seconds)
+    sensor.close()
+    del h_iq, d_iq, k
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs on the same box, same process (every rank takes part) ---------------
+    others = {}
+    if ACTIVE["name"] == "config2" and not args.no_others:
+        for label, (wname, env) in OTHER_WORKLOADS.items():
+            r = measure(ctx, wname, args.other_steps, 3, env=env)
+            others[label] = {"gsamples_s": r["value"], "scaling": r["scaling"], "kernel": r["kernel"], "kernel_ms": r["kernel_ms"],
+                             "ms_per_step": r["ms_per_step"], "steps": r["steps"], "frac": r["frac"],
+                             "achieved_gbs": r["achieved_gbs"], "samples_per_gpu": r["samples_per_gpu"],
+                             "total_samples": r["total_samples"], "traffic": kernel_traffic(r["kernel"]),
+                             "parity_check": r["parity_check"], "clocks": r["clocks"], "workload": r["workload"]}
+            if env:
+                others[label]["env"] = env
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same capture -----------------------
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        iq_host = h_iq.numpy().ravel() if cfg.iq_format == crn.IQ_SC16 else h_iq.numpy().view(np.complex64).ravel()
-        cpu = cpu_leg(crn, cfg, iq_host, args.cpu_seconds)
-    peak, peak_src = measured_peak()
-    kernel_ms = sum(step_ms) / len(step_ms)  # one launch per step: event-timed launch duration
-    achieved = nsamp * sample_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(), "kernel": info["name"], "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": nsamp * sample_bytes, "kernel_ms": kernel_ms,
-                "note": "%d B per complex sample read once;" % sample_bytes + " feature write-back (%d B per launch) not counted" %
-                        (ngroups * (cfg.nbands * 4 + 3 * 8 + 4 + 8))}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": base_config({"samples_per_gpu": nsamp, "groups_per_gpu": ngroups, "kernel": info,
-                                   "nfft": cfg.nfft, "navg": cfg.navg, "nbands": cfg.nbands}),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-            "cpu_baseline": cpu, "parity_check": parity, "decision_histogram": dec_hist.cpu().tolist(),
-            "ms_per_step_minmax": [min(step_ms), max(step_ms)]}
+    peak, peak_src = ctx.peak
+    roofline = {"bound": "hbm", "achieved": main["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": main["frac"],
+                "traffic": kernel_traffic(main["kernel"]), "kernel": main["kernel"], "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": nsamp * sample_bytes, "kernel_ms": main["kernel_ms"],
+                "note": "%d B per complex sample read once; kernel_ms = CUDA events around the launch alone; the feature "
+                        "write-back (%d B per launch) is not counted in the bytes; `value` additionally includes the "
+                        "device->host read of the results" % (sample_bytes, main["d2h_bytes_per_step"])}
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": main["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": base_config({"samples_per_gpu": nsamp, "groups_per_gpu": ngroups, "kernel": main["kernel_info"],
+                                   "nfft": cfg.nfft, "navg": cfg.navg, "nbands": cfg.nbands,
+                                   "timed_region": "per step: one fused launch + device->host copy of features, MLP outputs, decisions and masks"}),
+            "clocks": main["clocks"], "e2e": e2e, "gpu_launches": main["gpu_launches"], "roofline": roofline,
+            "cpu_baseline": cpu, "parity_check": main["parity_check"], "decision_histogram": dec_hist.cpu().tolist(),
+            "ms_per_step_minmax": main["kernel_ms_minmax"], "other_workloads": others}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -503,6 +616,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs appended to the default line")
+    ap.add_argument("--other-steps", type=int, default=5)
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: FFT size x batch frames, one JSON line with all rows")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
                     help="default = BASELINE configs[1] (the contract's bench line); others = remaining BASELINE configs")

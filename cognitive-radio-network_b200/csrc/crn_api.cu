@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <functional>
 #include <vector>
 
 #include "crn_internal.h"
@@ -140,32 +141,53 @@ void unpack_result(const ResultBuf &r, int64_t i, int nbands, uint64_t first_fra
   for (int b = 0; b < nbands; b++) out->feat[b] = r.h_feat[i * nbands + b];
 }
 
-// Inter-pass twiddle tables, computed in double.  Pass p (Ns = product of earlier radices, radix R)
-// multiplies input q of FFT column j by W(q, j) = exp(-j 2 pi q (j mod Ns) / (Ns R)).  The kernel reads only
-// q < R/2 (the partner q + R/2 is W(q) times a thread constant), two twiddles per 16-byte load:
-//   tw[(q/2)*Ns + jq] = { W(q, jq), W(q + 1, jq) },  q even < R/2, jq < Ns.
+// Tables of the twisted codelets (crn_fft_regs.cuh), computed in double.  A radix-R codelet whose inputs carry
+// w^q, w = exp(-j 2 pi phi), reads R/2 values  entry 0: w^(R/2);  entry m/4 + J: w^(R/m) W_m^J, J < m/4, m = 4..R,
+// two per 16-byte row:  tw[(e/2) * ncols + col] = { entry e, entry e + 1 }  as (re, im, re, im).
+void add_twisted_table(std::vector<float4> &tw, int r, int ncols, const std::function<double(int)> &phi_of_col) {
+  auto entry = [&](int e, double phi) {
+    int m = 2, j = 0;
+    if (e > 0) {
+      m = 4;
+      while (m / 2 <= e) m *= 2;  // e in [m/4, m/2)
+      j = e - m / 4;
+    }
+    const double turn = (double)(r / m) * phi + (double)j / (double)m;
+    const double a = -2.0 * M_PI * (turn - floor(turn));
+    return make_float2((float)cos(a), (float)sin(a));
+  };
+  for (int row = 0; row < r / 4; row++)
+    for (int col = 0; col < ncols; col++) {
+      const double phi = phi_of_col(col);
+      const float2 a = entry(2 * row, phi), b = entry(2 * row + 1, phi);
+      tw.push_back(make_float4(a.x, a.y, b.x, b.y));
+    }
+}
+// Pass p of a Stockham plan (Ns = product of earlier radices, radix R): column j has w = W_{Ns R}^(j mod Ns).
 void build_twiddles(const crn::RadixPlan &rp, std::vector<float4> &tw) {
   tw.clear();
-  auto add = [&](int ns, int r) {
-    const double step = -2.0 * M_PI / ((double)ns * (double)r);
-    for (int q = 0; q < r / 2; q += 2)
-      for (int jq = 0; jq < ns; jq++) {
-        const double a = step * (double)((long long)q * jq);
-        const double b = step * (double)((long long)(q + 1) * jq);
-        tw.push_back(make_float4((float)cos(a), (float)sin(a), (float)cos(b), (float)sin(b)));
-      }
-  };
   if (rp.hybrid) {
-    // hybrid plan: the 1024-point 32x32 table, then W_N^n for n < 1024 (1024 float2 packed as 512 float4)
-    add(32, 32);
-    for (int n = 0; n < 1024; n += 2) {
-      const double a0 = -2.0 * M_PI * (double)n / (double)rp.n, a1 = -2.0 * M_PI * (double)(n + 1) / (double)rp.n;
-      tw.push_back(make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1)));
-    }
+    // hybrid plan N = C * 1024 (crn_sense_kernel.cuh).  Pass C, FOLD_C: column t = 32 r + lane, w = W_N^(C lane + r);
+    // otherwise column lane, w = W_1024^lane.  Then pass B, column r: w = W_N^(32 r); without FOLD_C followed by
+    // { u, u w^16 } per team thread t = 32 r + lane, u = W_N^(lane r).
+    const int c = rp.n / 1024;
+    if (rp.fold_c)
+      add_twisted_table(tw, 32, 32 * c, [&](int t) { return (double)(c * (t & 31) + (t >> 5)) / (double)rp.n; });
+    else
+      add_twisted_table(tw, 32, 32, [&](int j) { return (double)j / 1024.0; });
+    add_twisted_table(tw, 32, c, [&](int r) { return (double)(32 * r) / (double)rp.n; });
+    if (!rp.fold_c)
+      for (int t = 0; t < 32 * c; t++) {
+        const int lane = t & 31, r = t >> 5;
+        const double au = -2.0 * M_PI * (double)(lane * r) / (double)rp.n;
+        const double av = au - 2.0 * M_PI * (double)((16 * 32 * r) % rp.n) / (double)rp.n;
+        tw.push_back(make_float4((float)cos(au), (float)sin(au), (float)cos(av), (float)sin(av)));
+      }
     return;
   }
-  add(rp.r0, rp.r1);
-  if (rp.r2 > 1) add(rp.r0 * rp.r1, rp.r2);
+  add_twisted_table(tw, rp.r1, rp.r0, [&](int j) { return (double)j / (double)(rp.r0 * rp.r1); });
+  if (rp.r2 > 1)
+    add_twisted_table(tw, rp.r2, rp.r0 * rp.r1, [&](int j) { return (double)j / (double)(rp.r0 * rp.r1 * rp.r2); });
 }
 
 // Window in the kernel's register order: thread t of a team holds points t + T*m; the first butterfly
@@ -176,8 +198,11 @@ void build_window_pairs(const crn::RadixPlan &rp, std::vector<float2> &wp) {
   std::vector<float> w(N);
   for (int n = 0; n < N; n++) w[n] = 0.5f - 0.5f * cosf((float)(2.0 * M_PI * (double)n) / (float)(N - 1));
   wp.resize(N / 2);
+  // own-share hybrid plan (N = 2048): the threads of warp 1 (t >= 32) compute the radix-2 difference in the "sum"
+  // register, i.e. their second weight carries a minus sign
   for (int m = 0; m < E / 2; m++)
-    for (int t = 0; t < T; t++) wp[m * T + t] = make_float2(w[t + T * m], w[t + T * (m + E / 2)]);
+    for (int t = 0; t < T; t++)
+      wp[m * T + t] = make_float2(w[t + T * m], (rp.own_share && t >= 32 ? -1.0f : 1.0f) * w[t + T * (m + E / 2)]);
 }
 
 // Reduction units per decision group: the divisor of `units` that balances the K frames best over the

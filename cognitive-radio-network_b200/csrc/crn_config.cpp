@@ -81,19 +81,19 @@ int crn_config_reference(crn_config *c) {
 
 int crn_config_welch(crn_config *c, int32_t nfft, int32_t navg) {
   if (!c) return crn::fail(CRN_ERR_INVALID, "crn_config_welch: null config");
-  if (!is_pow2(nfft) || nfft < 512 || nfft > 8192 || navg < 1)
-    return crn::fail(CRN_ERR_INVALID, "crn_config_welch: nfft must be a power of two in [512,8192], navg >= 1");
+  if (!is_pow2(nfft) || nfft < 256 || nfft > 8192 || navg < 1)
+    return crn::fail(CRN_ERR_INVALID, "crn_config_welch: nfft must be a power of two in [256,8192], navg >= 1");
   crn_config_reference(c);
-  const int scale = nfft / 512;  // same Hz edges: bin width shrinks by `scale`
   c->nfft = nfft;
   c->frame_len = nfft;
   c->navg = navg;
   c->window = CRN_WINDOW_HANN;
   c->detector = CRN_DET_MAGSQ;
   c->postop = CRN_POST_SUM;
+  // same Hz edges: bin indices scale with nfft / 512 (rounded down at N = 256, where the bins are twice as wide)
   for (int s = 0; s < c->nsegs; s++) {
-    c->segs[s].lo *= scale;
-    c->segs[s].hi *= scale;
+    c->segs[s].lo = (int)((long long)c->segs[s].lo * nfft / 512);
+    c->segs[s].hi = (int)((long long)c->segs[s].hi * nfft / 512);
   }
   return CRN_OK;
 }

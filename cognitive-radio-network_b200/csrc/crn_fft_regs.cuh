@@ -170,6 +170,51 @@ __device__ __forceinline__ void fft_dit(float2 (&v)[R]) {
   });
 }
 
+// Butterfly with a run-time twiddle tau = (c, -s) held in registers: 3 packed instructions.
+__device__ __forceinline__ void butterfly_rt(float2 &a, float2 &b, float c, float s) {
+  float2 p = fma2(b, bc2(c), a);
+  p = fma2(mulnegj(b), bc2(s), p);
+  b = fma2(a, bc2(2.0f), neg2(p));
+  a = p;
+}
+
+// "Twisted" radix-R DIT codelet: the inter-pass twiddles w^q of a Stockham pass (input q of the column is
+// multiplied by w^q, w a per-thread constant) are not applied to the inputs; they ride on the butterflies:
+//     X[k] = sum_q x_q w^q W_R^(qk)   =>   stage m = 2^S multiplies by  tau_m[J] = w^(R/m) W_m^J  instead of W_m^J.
+// Every butterfly then has a run-time twiddle (3 packed instructions, none trivial), but there is no separate
+// twiddle layer: a radix-32 pass costs 240 packed instructions against 194 + 62 (+ the table reads of 31 twiddles).
+// tau_m[J + m/4] = -j tau_m[J], so a stage needs max(1, m/4) table values: R/2 in all, laid out stage by stage
+//     entry 0: tau_2[0];  entry m/4 + J: tau_m[J], J < m/4  (m >= 4),
+// two entries per 16-byte table row:  col[(e/2) * RS] = { tau_e, tau_(e+1) }  as (re, im, re, im).
+// On entry v[i] = x[bitrev(i)]; FIRST = 2 skips stage 1 (done by the caller).
+template <int RS>
+struct TwistedTable {
+  const float4 *__restrict__ col;  // this thread's column of the table; rows are RS float4 apart
+  template <int E>
+  __device__ __forceinline__ float2 entry() const {
+    const float4 w = col[(E / 2) * RS];
+    return (E & 1) ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
+  }
+};
+template <int R, int FIRST, int RS>
+__device__ __forceinline__ void fft_dit_twisted(float2 (&v)[R], const TwistedTable<RS> tw) {
+  constexpr int LOG = ilog2(R);
+  static_for<FIRST, LOG + 1>([&](auto S) {
+    constexpr int m = 1 << S.value;
+    constexpr int h = m >> 1;
+    constexpr int cnt = (m >= 4) ? m / 4 : 1;
+    constexpr int base = (m >= 4) ? m / 4 : 0;
+    static_for<0, cnt>([&](auto J) {
+      const float2 tau = tw.template entry<base + J.value>();
+      static_for<0, R / m>([&](auto B) {
+        constexpr int k = B.value * m + J.value;
+        butterfly_rt(v[k], v[k + h], tau.x, -tau.y);
+        if constexpr (m >= 4) butterfly_rt(v[k + cnt], v[k + cnt + h], tau.y, tau.x);  // -j tau
+      });
+    });
+  });
+}
+
 // a * w (complex): 2 packed instructions
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
   return fma2(mulnegj(a), bc2(-w.y), mul2(a, bc2(w.x)));

@@ -97,16 +97,16 @@ int launch_sense_8192(const SenseParams &, int, int, int, cudaStream_t, LaunchGe
 
 // Radix plan per size (must match the Plan<> in crn_sense_n<N>.cu): the host builds the paired twiddle
 // and window tables from it.
-struct RadixPlan { int n, e, r0, r1, r2; bool hybrid; };
+struct RadixPlan { int n, e, r0, r1, r2; bool hybrid; bool fold_c; bool own_share; };
 inline RadixPlan radix_plan(int n) {
   switch (n) {
-    case 256: return {256, 16, 16, 16, 1, false};
-    case 512: return {512, 32, 32, 16, 1, false};
-    case 1024: return {1024, 32, 32, 32, 1, false};
-    case 2048: return {2048, 32, 2, 32, 32, true};
-    case 4096: return {4096, 32, 4, 32, 32, true};
-    case 8192: return {8192, 32, 8, 32, 32, true};
-    default: return {0, 0, 0, 0, 0, false};
+    case 256: return {256, 16, 16, 16, 1, false, false, false};
+    case 512: return {512, 32, 32, 16, 1, false, false, false};
+    case 1024: return {1024, 32, 32, 32, 1, false, false, false};
+    case 2048: return {2048, 32, 2, 32, 32, true, HybridPlan<2048, 1, 1>::FOLD_C, HybridPlan<2048, 1, 1>::OWN_SHARE};
+    case 4096: return {4096, 32, 4, 32, 32, true, HybridPlan<4096, 1, 1>::FOLD_C, HybridPlan<4096, 1, 1>::OWN_SHARE};
+    case 8192: return {8192, 32, 8, 32, 32, true, HybridPlan<8192, 1, 1>::FOLD_C, HybridPlan<8192, 1, 1>::OWN_SHARE};
+    default: return {0, 0, 0, 0, 0, false, false, false};
   }
 }
 

@@ -82,8 +82,8 @@ struct Plan {
   static constexpr int PASSES = (R2 > 1) ? 3 : 2;
   static constexpr int PADSHIFT = ilog2(R0);       // two pad slots per R0 points: conflict-free, 16 B rows
   static constexpr int XSZ = N + 2 * (N >> PADSHIFT);  // float2 slots per team exchange buffer
-  static constexpr int TW1 = R0 * R1 / 4;          // pass-1 twiddle table entries (float4 = two twiddles)
-  static constexpr int TW2 = (R2 > 1) ? N / 4 : 0; // pass-2 twiddle table entries (float4 = two twiddles)
+  static constexpr int TW1 = R0 * R1 / 4;          // pass-1 twisted-codelet table: R1/4 rows of R0 columns (float4)
+  static constexpr int TW2 = (R2 > 1) ? N / 4 : 0; // pass-2 table: R2/4 rows of R0*R1 columns
   static constexpr int UNIT_THREADS = T > 32 ? T : 32;
   static constexpr int UNITS = NT / UNIT_THREADS;  // reduction units per CTA
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
@@ -122,13 +122,15 @@ struct Plan {
 
 // Plan for N = C * 1024, C in {2, 4, 8}: "one cross-warp step, then every warp on its own".
 //   pass A   radix-C decimation in frequency across the frame's C 1024-sample segments (registers
-//            {i + r*G}, G = 32/C; window folded in), then the DIF twiddles W_N^(n r) - built from ONE table
-//            value W_N^n per n by squaring/multiplying, so the table is 8 KB whatever N is;
-//   exchange the only team-wide one: sub-sequence y_r goes to warp r;
-//   pass B,C warp r runs the 1024-point 32x32 FFT of y_r with warp-local synchronisation only, exactly as
-//            the N = 1024 kernel does; it ends up holding bins C*k + r.
+//            {i + r*G}, G = 32/C; window folded in): z_r[n], n < 1024;
+//   exchange the only team-wide one: z_r goes to warp r;
+//   pass B,C warp r runs the 1024-point 32x32 FFT of y_r[n] = z_r[n] W_N^(n r) with warp-local synchronisation only
+//            and ends up holding bins C*k + r.  Both passes use twisted codelets (crn_fft_regs.cuh), and the DIF
+//            twiddles W_N^(n r) cost nothing: with n = j + 32 q they split into (W_N^(32 r))^q - pass B's per-warp
+//            w - and W_N^(j r), which multiplies pass C's input j and so merges with its W_1024^(j k):
+//            w = W_N^(C k + r), one table column per team thread.
 // Against the generic three-pass plans this halves the multi-warp barriers per frame, needs ~128 instead of
-// 170-230 registers and a third less shared memory (two CTAs per SM at N = 8192).
+// 170-230 registers and a third less shared memory.
 template <int N_, int TEAMS_, int MINB_>
 struct HybridPlan {
   static constexpr int N = N_, E = 32, TEAMS = TEAMS_, MINB = MINB_;
@@ -140,8 +142,26 @@ struct HybridPlan {
   static constexpr int PADSHIFT = 5;
   static constexpr int RS = 32 * (32 + 2);         // float2 slots of one warp's region (padded 32x32 exchange)
   static constexpr int XSZ = C * RS;
-  static constexpr int TW1 = 256;                  // 32x32 twiddles of the 1024-point FFT, first half (float4)
-  static constexpr int TW2 = 512;                  // W_N^n, n < 1024, as 1024 float2 = 512 float4
+  // Where the q-independent part W_N^(j r) of the DIF twiddles goes (see above).  FOLD_C: into pass C's w - free, but
+  // the pass-C table then has one column per team thread (128 T bytes: 32 KB at N = 8192, which pushes the CTA past
+  // the 196 KB shared-memory carve-out and leaves the SM with a 28 KB L1: measured -8 %).  !FOLD_C (N = 8192): pass B
+  // multiplies its column by u = W_N^(j r) in its first stage (+32 packed instructions per frame and thread, one
+  // 16-byte read of {u, u w^16}); pass C then uses the 4 KB table of the 1024-point FFT.
+#if defined(CRN_FOLD_C_ALL)   // A/B switches (build.py --variant)
+  static constexpr bool FOLD_C = true;
+#elif defined(CRN_FOLD_B_ALL)
+  static constexpr bool FOLD_C = false;
+#else
+  static constexpr bool FOLD_C = (C < 8);
+#endif
+  // C = 2: each warp keeps its own half of pass A's outputs (see the kernel); -DCRN_NO_OWN_SHARE: A/B switch
+#ifdef CRN_NO_OWN_SHARE
+  static constexpr bool OWN_SHARE = false;
+#else
+  static constexpr bool OWN_SHARE = (C == 2);
+#endif
+  static constexpr int TW1 = FOLD_C ? 8 * T : 8 * 32;  // pass-C twisted-codelet table: 8 rows, one column per team thread / lane
+  static constexpr int TW2 = 8 * C + (FOLD_C ? 0 : T);  // pass-B table: 8 rows, one column per warp (+ {u, u w^16} per thread)
   static constexpr int UNIT_THREADS = T;
   static constexpr int UNITS = TEAMS;
   static constexpr int TEAMS_PER_UNIT = 1;
@@ -272,68 +292,46 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
   });
 }
 
-// Pass p >= 1: inter-pass twiddles W_{Ns*R}^{q*(j mod Ns)}, j = t + T*i, folded into the first stage.
-// The stage pairs inputs q and q + R/2, and W(q + R/2) = W(q) * W(R/2) with W(R/2) = exp(-j pi (j mod Ns)/Ns)
-// the same for every q: a thread constant (`half`, one per codelet, computed once per kernel).  So only the
-// first R/2 twiddles come from shared memory - twp[(q/2)*NS + (j mod NS)] = {W(q), W(q+1)}, q even < R/2 -
-// and the partner costs one packed complex multiply: half the table wavefronts for 2 instructions per pair.
-template <int E, int R, int T, int NS>
-__device__ __forceinline__ void reg_pass_tw(float2 (&a)[E], const float4 *__restrict__ twp, int t,
-                                            const float2 (&half)[E / R]) {
+// Pass p >= 1 of a Stockham plan (Ns = product of earlier radices): input q of column j = t + T*i carries the
+// inter-pass twiddle W_{Ns*R}^(q (j mod Ns)) = w^q.  The codelet is "twisted" (crn_fft_regs.cuh): the twiddles ride
+// on its butterflies, so the pass is R/2 log2(R) three-instruction butterflies and R/4 16-byte table reads per
+// column - no separate twiddle layer.  `col0` is the table column of codelet 0; codelet i reads column
+// col0[(T*i) & (NS-1)] (rows are RS float4 apart).
+// PRESCALE: the whole column is also multiplied by a per-thread constant u (`usc` = {u, u w^(R/2)}); that costs two
+// more packed instructions per first-stage butterfly (A = u a, p = A + (u tau) b, q = 2A - p).
+template <int E, int R, int T, int NS, int RS, bool PRESCALE = false>
+__device__ __forceinline__ void reg_pass_twisted(float2 (&a)[E], const float4 *__restrict__ twp, int t,
+                                                 const float4 *__restrict__ usc = nullptr) {
   constexpr int G = E / R;
   constexpr int LOG = ilog2(R);
   static_for<0, G>([&](auto I) {
-    const int jq = (t + T * I.value) & (NS - 1);
+    const TwistedTable<RS> tw{twp + ((t + T * I.value) & (NS - 1))};
     float2 v[R];
-    static_for<0, R / 4>([&](auto Q2) {
-      const float4 w = twp[Q2.value * NS + jq];
-      static_for<0, 2>([&](auto H) {
-        constexpr int q = 2 * Q2.value + H.value;
-        constexpr int m0 = I.value + q * G;
-        constexpr int br = bitrev(q, LOG);
-        const float2 wa = H.value ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
-        if constexpr (q == 0) {
-          butterfly_w_cplx<true>(a[m0], a[m0 + E / 2], wa, half[I.value], v[br], v[br + 1]);
-        } else {
-          butterfly_w_cplx<false>(a[m0], a[m0 + E / 2], wa, cmul(wa, half[I.value]), v[br], v[br + 1]);
-        }
+    if constexpr (PRESCALE) {
+      const float4 uu = *usc;
+      static_for<0, R / 2>([&](auto Q) {
+        constexpr int m0 = I.value + Q.value * G;
+        constexpr int br = bitrev(Q.value, LOG);
+        butterfly_w_cplx<false>(a[m0], a[m0 + E / 2], make_float2(uu.x, uu.y), make_float2(uu.z, uu.w), v[br], v[br + 1]);
       });
+    } else {
+    const float2 tau = tw.template entry<0>();  // w^(R/2): every first-stage butterfly
+    static_for<0, R / 2>([&](auto Q) {
+      constexpr int m0 = I.value + Q.value * G;  // partner is register m0 + E/2
+      constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
+      v[br] = a[m0];
+      v[br + 1] = a[m0 + E / 2];
+      butterfly_rt(v[br], v[br + 1], tau.x, -tau.y);
     });
-    fft_dit<R, 2>(v);
+    }
+    fft_dit_twisted<R, 2, RS>(v, tw);
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
-}
-// half[i] = exp(-j pi ((t + T i) mod NS) / NS); the argument is dyadic, sincospif is exact at it.
-template <int E, int R, int T, int NS>
-__device__ __forceinline__ void half_turn_twiddles(float2 (&half)[E / R], int t) {
-#pragma unroll
-  for (int i = 0; i < E / R; i++) {
-    float sn, cs;
-    sincospif((float)((t + T * i) & (NS - 1)) * (1.0f / (float)NS), &sn, &cs);
-    half[i] = make_float2(cs, -sn);
-  }
 }
 
 // Exchange rows are padded by two points: rows stay 16-byte aligned for the 16-byte stores of pass 0 and
 // consecutive rows land in different banks (row stride 34 or 18 points -> conflict-free quarter-warps).
 #define CRN_XPAD 2
-// DIF twiddles of the hybrid plan: register i + r*G holds z_r[n] with n = t + T*i; multiply by W_N^(n r).
-// Only W_N^n comes from the table; the powers are built by squaring / one multiplication each.
-template <int E, int C, int T>
-__device__ __forceinline__ void hybrid_twiddle(float2 (&a)[E], const float2 *__restrict__ twA, int t) {
-  constexpr int G = E / C;
-  static_for<0, G>([&](auto I) {
-    const float2 w1 = twA[t + T * I.value];
-    float2 w[C];
-    w[1] = w1;
-    static_for<2, C>([&](auto R) {
-      if constexpr (R.value % 2 == 0) w[R.value] = cmul(w[R.value / 2], w[R.value / 2]);
-      else w[R.value] = cmul(w[R.value - 1], w1);
-    });
-    static_for<1, C>([&](auto R) { a[I.value + R.value * G] = cmul(a[I.value + R.value * G], w[R.value]); });
-  });
-}
-
 template <int PADSHIFT>
 __device__ __forceinline__ int xphys(int idx) {
   return idx + CRN_XPAD * (idx >> PADSHIFT);
@@ -498,14 +496,6 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
   }
   __syncthreads();
 
-  // thread-constant half-turn twiddles of the later passes (see reg_pass_tw)
-  constexpr int HR1 = P::HYBRID ? 32 : P::R1, HNS1 = P::HYBRID ? 32 : P::R0, HT1 = P::HYBRID ? 32 : T;
-  float2 half1[E / HR1];
-  half_turn_twiddles<E, HR1, HT1, HNS1>(half1, P::HYBRID ? (t & 31) : t);
-  constexpr int HR2 = (!P::HYBRID && P::PASSES == 3) ? P::R2 : E;
-  float2 half2[E / HR2];
-  if constexpr (!P::HYBRID && P::PASSES == 3) half_turn_twiddles<E, HR2, T, P::R0 * P::R1>(half2, t);
-
   const int L = prm.L, K = prm.K;
   const bool full = (L == N);
   // Work items (see "Group splitting" above).  The all-bins kernels sit exactly at the register cap, so the item
@@ -566,28 +556,70 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       }
       if constexpr (P::HYBRID) {
         constexpr int C = P::C, G = E / C;
-        // pass A: radix-C across the frame's C segments (window folded in), then the DIF twiddles
+        // pass A: radix-C across the frame's C segments (window folded in).  The DIF twiddles W_N^(n r) that turn
+        // its outputs z_r[n] into the sub-sequences y_r[n] are not applied here: with n = j + 32 q they factor into
+        // (W_N^(32 r))^q, which rides on pass B's butterflies, and W_N^(j r), which joins pass C's w.
+        const int lane = t & 31;
+        float2 *wb = xb + (t >> 5) * P::RS;
+        if constexpr (P::OWN_SHARE) {
+          // C = 2: a thread of warp w keeps the half of its outputs that belongs to its own warp (z_w) and hands
+          // only the other half to the partner warp: half the exchange traffic (16 stores + 16 loads instead of 32
+          // + 32).  Both warps run the same straight-line code:
+          //  * the sign of the radix-2 butterfly is a per-thread constant (baked into the window pairs), so the
+          //    "sum" register always holds z_w[n] and the "difference" register z_(1-w)[n];
+          //  * warp 1 transforms its sub-sequence circularly shifted by 32 samples, y'_1[n'] = y_1[n' + 32] (|Y| is
+          //    unchanged, the bins keep their places), so in BOTH warps the kept values are pass B's even inputs
+          //    q = 2i and the received ones the odd inputs: warp 0 stores value i into slot i - 1 (mod 16) of warp
+          //    1's region, negating the wrapped one (W_N^(n + 1024) = -W_N^n), warp 1 stores value i into slot i.
+          const int w = t >> 5;
+          const float sg = w ? -1.0f : 1.0f;
+          static_for<0, E / 2>([&](auto I) {
+            float2 p, q;
+            if constexpr (WIN) {
+              const float2 wp = winp[I.value * T + t];  // { w[n], (+/-) w[n + N/2] }
+              butterfly_w_real(a[I.value], a[I.value + E / 2], wp.x, wp.y, p, q);
+            } else {
+              p = fma2(a[I.value + E / 2], bc2(sg), a[I.value]);
+              q = fma2(a[I.value + E / 2], bc2(-sg), a[I.value]);
+            }
+            a[I.value] = p;
+            a[I.value + E / 2] = q;
+          });
+          a[E / 2] = mul2(a[E / 2], bc2(-sg));  // warp 0: the value that wraps around in warp 1's shifted sequence
+          float2 *theirs = xb + (1 - w) * P::RS + lane;
+          team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
+          theirs[w ? 0 : 32 * 15] = a[E / 2];
+          static_for<1, E / 2>([&](auto I) { (theirs - (w ? 0 : 32))[32 * I.value] = a[I.value + E / 2]; });
+          team_sync<T>(team);
+          static_for<0, E / 2>([&](auto I) {  // descending: a[2i] = a[i] must not overwrite a value still needed
+            constexpr int i = E / 2 - 1 - I.value;
+            a[2 * i] = a[i];
+          });
+          static_for<0, E / 2>([&](auto I) { a[2 * I.value + 1] = wb[lane + 32 * I.value]; });
+        } else {
         reg_pass_first<E, C, T, WIN>(a, winp, t);
-        hybrid_twiddle<E, C, T>(a, reinterpret_cast<const float2 *>(tw2), t);
         // the one team-wide exchange: y_r[n] (n = t + T*i) goes to warp r's region, linear in n
         team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
         static_for<0, G>([&](auto I) {
           static_for<0, C>([&](auto R) { xb[R.value * P::RS + t + T * I.value] = a[I.value + R.value * G]; });
         });
         team_sync<T>(team);
-        const int lane = t & 31;
-        float2 *wb = xb + (t >> 5) * P::RS;
 #pragma unroll
         for (int m = 0; m < E; m++) a[m] = wb[lane + 32 * m];
+        }
         // warp r: 1024-point FFT of y_r, warp-local from here on (same code as the N = 1024 kernel)
         __syncwarp();  // the region is rewritten in padded layout below
-        reg_pass_first<E, 32, 32, false>(a, winp, lane);
+        // pass B: column j = lane, input q carries (W_N^(32 r))^q - the same w for the whole warp (table column r)
+        if constexpr (P::FOLD_C) reg_pass_twisted<E, 32, 32, 1, C>(a, tw2 + (t >> 5), 0);
+        else reg_pass_twisted<E, 32, 32, 1, C, true>(a, tw2 + (t >> 5), 0, tw2 + 8 * C + t);
         exchange<E, 32, 32, 1, 5>(a, wb, lane, 0);
         if (tma && k + FT < KP) {
           team_sync<T>(team);  // every warp of the team has gathered its points: the regions are idle
           if (t == 0) tma_load_frame(xb, x + fstep, frame_bytes, &mbars[team]);
         }
-        reg_pass_tw<E, 32, 32, 32>(a, tw1, lane, half1);
+        // pass C: input q carries W_1024^(q lane) W_N^(q r) = (W_N^(C lane + r))^q: table column t = 32 r + lane
+        if constexpr (P::FOLD_C) reg_pass_twisted<E, 32, T, T, T>(a, tw1, t);
+        else reg_pass_twisted<E, 32, 32, 32, 32>(a, tw1, lane);
       } else {
       // pass 0 (Ns = 1: no twiddles; window folded in)
       reg_pass_first<E, P::R0, T, WIN>(a, winp, t);
@@ -602,11 +634,11 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       };
       if constexpr (P::PASSES == 2) stage_next();
       // pass 1
-      reg_pass_tw<E, P::R1, T, P::R0>(a, tw1, t, half1);
+      reg_pass_twisted<E, P::R1, T, P::R0, P::R0>(a, tw1, t);
       if constexpr (P::PASSES == 3) {
         exchange<E, P::R1, T, P::R0, P::PADSHIFT>(a, xb, t, team);
         stage_next();
-        reg_pass_tw<E, P::R2, T, P::R0 * P::R1>(a, tw2, t, half2);
+        reg_pass_twisted<E, P::R2, T, P::R0 * P::R1, P::R0 * P::R1>(a, tw2, t);
       }
       }  // !HYBRID
       // register m now holds bin P::bin_of(t, m)  (.cpp:152-154)

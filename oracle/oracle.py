@@ -19,6 +19,72 @@ REF_PATH = os.path.join(HERE, "_ref", "libcrn_ref.so")
 
 _port = None
 _ref = None
+_native = None
+
+# ---- the oracle's own mirror of include/crnsense.h's crn_config / crn_synth_config (layout only): the reference
+# arm of bench.py builds its workloads from these and crn_oracle_config.c, without loading the product library.
+MAX_BANDS, MAX_SEGS = 64, 128
+
+
+class Seg(C.Structure):
+    _fields_ = [("band", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("nfft", C.c_int32), ("frame_len", C.c_int32), ("frame_stride", C.c_int32), ("navg", C.c_int32),
+        ("window", C.c_int32), ("detector", C.c_int32), ("postop", C.c_int32), ("decide", C.c_int32),
+        ("nbands", C.c_int32), ("nsegs", C.c_int32), ("segs", Seg * MAX_SEGS),
+        ("ann_wih", (C.c_double * 6) * 5), ("ann_who", (C.c_double * 4) * 6),
+        ("ann_threshold", C.c_double), ("energy_factor", C.c_double),
+        ("device", C.c_int32), ("ring_slots", C.c_int32), ("iq_format", C.c_int32), ("reserved_", C.c_int32),
+    ]
+
+    @property
+    def group_samples(self):
+        return (self.frame_stride if self.frame_stride > 0 else self.frame_len) * self.navg
+
+
+class SynthConfig(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("fs", C.c_double), ("pu_rate", C.c_double), ("offsets_hz", C.c_double * 3),
+        ("snr_db", C.c_double), ("pu_gain_db", C.c_double), ("hop_mode", C.c_int32),
+        ("dwell_groups", C.c_int32), ("group_samples", C.c_int32),
+        ("intf_type", C.c_int32), ("intf_period_groups", C.c_int32), ("reserved_", C.c_int32),
+        ("intf_offset_hz", C.c_double), ("intf_rate", C.c_double), ("intf_gain_db", C.c_double),
+        ("intf_duty", C.c_double),
+    ]
+
+
+def config_reference():
+    c = Config()
+    port().crn_oracle_config_reference(C.byref(c))
+    return c
+
+
+def config_welch(nfft, navg):
+    c = Config()
+    assert port().crn_oracle_config_welch(C.byref(c), nfft, navg) == 0, (nfft, navg)
+    return c
+
+
+def config_wideband(nfft, navg, nch):
+    c = Config()
+    assert port().crn_oracle_config_wideband(C.byref(c), nfft, navg, nch) == 0, (nfft, navg, nch)
+    return c
+
+
+def synth_config(group_samples, **kw):
+    sc = SynthConfig()
+    port().crn_oracle_synth_config_default(C.byref(sc), group_samples)
+    for k, v in kw.items():
+        if k == "offsets_hz":
+            for i, x in enumerate(v):
+                sc.offsets_hz[i] = x
+        else:
+            assert hasattr(sc, k), k
+            setattr(sc, k, v)
+    return sc
 
 
 def build():
@@ -26,39 +92,64 @@ def build():
     subprocess.run(["make", "-s", "-C", HERE], check=True, capture_output=True)
 
 
+def _declare(lib):
+    lib.crn_oracle_sense.restype = C.c_int
+    lib.crn_oracle_sense.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int]
+    lib.crn_oracle_time.restype = C.c_double
+    lib.crn_oracle_time.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.crn_oracle_max_threads.restype = C.c_int
+    lib.crn_oracle_hann.restype = C.c_float
+    lib.crn_oracle_hann.argtypes = [C.c_int, C.c_int]
+    lib.crn_oracle_stream_seed.restype = C.c_uint64
+    lib.crn_oracle_stream_seed.argtypes = [C.c_uint64, C.c_int64]
+    lib.crn_oracle_pu_states.restype = None
+    lib.crn_oracle_pu_states.argtypes = [C.c_uint64, C.c_int, C.c_int64, C.c_void_p]
+    lib.crn_oracle_pu_next.restype = C.c_int
+    lib.crn_oracle_pu_next.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.crn_oracle_synth.restype = None
+    lib.crn_oracle_synth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    lib.crn_oracle_synth_sigma2.restype = C.c_double
+    lib.crn_oracle_synth_sigma2.argtypes = [C.c_void_p]
+    lib.crn_oracle_ann_forward.restype = None
+    lib.crn_oracle_ann_forward.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.crn_oracle_ann_error.restype = C.c_double
+    lib.crn_oracle_ann_error.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.crn_oracle_ann_train.restype = C.c_int
+    lib.crn_oracle_ann_train.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    lib.crn_oracle_config_reference.restype = None
+    lib.crn_oracle_config_reference.argtypes = [C.c_void_p]
+    lib.crn_oracle_config_welch.restype = C.c_int
+    lib.crn_oracle_config_welch.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.crn_oracle_config_wideband.restype = C.c_int
+    lib.crn_oracle_config_wideband.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.crn_oracle_synth_config_default.restype = None
+    lib.crn_oracle_synth_config_default.argtypes = [C.c_void_p, C.c_int32]
+    return lib
+
+
 def port():
     global _port
     if _port is None:
         if not os.path.exists(PORT_PATH):
             build()
-        lib = C.CDLL(PORT_PATH)
-        lib.crn_oracle_sense.restype = C.c_int
-        lib.crn_oracle_sense.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_void_p, C.c_int]
-        lib.crn_oracle_time.restype = C.c_double
-        lib.crn_oracle_time.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
-        lib.crn_oracle_max_threads.restype = C.c_int
-        lib.crn_oracle_hann.restype = C.c_float
-        lib.crn_oracle_hann.argtypes = [C.c_int, C.c_int]
-        lib.crn_oracle_stream_seed.restype = C.c_uint64
-        lib.crn_oracle_stream_seed.argtypes = [C.c_uint64, C.c_int64]
-        lib.crn_oracle_pu_states.restype = None
-        lib.crn_oracle_pu_states.argtypes = [C.c_uint64, C.c_int, C.c_int64, C.c_void_p]
-        lib.crn_oracle_pu_next.restype = C.c_int
-        lib.crn_oracle_pu_next.argtypes = [C.c_int, C.c_int, C.c_int]
-        lib.crn_oracle_synth.restype = None
-        lib.crn_oracle_synth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
-        lib.crn_oracle_synth_sigma2.restype = C.c_double
-        lib.crn_oracle_synth_sigma2.argtypes = [C.c_void_p]
-        lib.crn_oracle_ann_forward.restype = None
-        lib.crn_oracle_ann_forward.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
-        lib.crn_oracle_ann_error.restype = C.c_double
-        lib.crn_oracle_ann_error.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
-        lib.crn_oracle_ann_train.restype = C.c_int
-        lib.crn_oracle_ann_train.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
-                                             C.POINTER(C.c_double), C.POINTER(C.c_int32)]
-        _port = lib
+        _port = _declare(C.CDLL(PORT_PATH))
     return _port
+
+
+def native():
+    """The port compiled -O3 -march=native ON THIS HOST (timing only; bench.py's cpu_baseline).  None if it cannot
+    be built here."""
+    global _native
+    if _native is None:
+        out = os.path.join("/tmp", "crn_oracle_native_%d" % os.getuid())
+        try:
+            subprocess.run(["make", "-s", "-C", HERE, "native", "NATIVE_OUT=" + out], check=True, capture_output=True)
+            _native = _declare(C.CDLL(os.path.join(out, "liboracle_native.so")))
+        except (OSError, subprocess.CalledProcessError):
+            _native = False
+    return _native or None
 
 
 def ref():
@@ -106,9 +197,16 @@ def sense_port(cfg, iq, ngroups=None, nthreads=1):
     return feat, ann, dec, mask
 
 
-def time_port(cfg, iq, ngroups, nthreads):
+def time_port(cfg, iq, ngroups, nthreads, lib=None):
     iq = np.ascontiguousarray(iq, dtype=np.int16) if getattr(cfg, "iq_format", 0) == 1 else _iq_f32(iq)
-    return port().crn_oracle_time(C.byref(cfg), iq.ctypes.data, ngroups, nthreads)
+    return (lib or port()).crn_oracle_time(C.byref(cfg), iq.ctypes.data, ngroups, nthreads)
+
+
+def fftw_installed():
+    """Is an FFTW3 single-precision library on this host?  (liquid-dsp can be configured on top of it; the restated
+    radix-2 FFT of the port is what liquid does without it.)  Reported in cpu_baseline.sample, nothing links it."""
+    import ctypes.util
+    return ctypes.util.find_library("fftw3f") is not None
 
 
 def sense_ref(iq, L=512, want_bins=False):
