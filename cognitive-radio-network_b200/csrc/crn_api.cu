@@ -82,6 +82,14 @@ struct crn_handle {
   // (40 vs 43 us at 512 KiB, 27 vs 30 us at 40 KiB).  CRN_RING_COPY=1 / 0 forces the copy / the direct read (A/B).
   bool ring_zero_copy = false;
   SplitBuf host_split, dev_split;  // batch-host pipeline (h->stream) / batch-device launches (caller's stream)
+  // Both are allocated at crn_create for the largest batch that is ever split (split_max_groups), so no launch
+  // allocates or synchronises (crn_sense_batch_device stays asynchronous and legal under stream capture).  dev_split is
+  // shared by the caller's streams: a split launch records dev_split_event, and a later split launch on a DIFFERENT
+  // stream first waits for it, so two streams never share the arrival counters.
+  int64_t split_max_groups = 0;
+  cudaEvent_t dev_split_event = nullptr;
+  cudaStream_t dev_split_stream = nullptr;
+  bool dev_split_used = false;
   cudaStream_t stream = nullptr;     // streaming path + batch_host compute
   cudaStream_t copy_stream = nullptr;
   int64_t launches = 0;
@@ -235,7 +243,7 @@ int grid_for(const crn_handle *h, int64_t nwork) {
 // team and item, that minimises rounds x (frames per team and item + epilogue), the epilogue counted as two
 // frames.  Many groups -> 1 (nothing to gain); one decision on the streaming path -> as many items as K allows.
 int pick_split(const crn_handle *h, int64_t ngroups) {
-  if (h->base.upg != 0) return 1;
+  if (h->base.upg != 0 || ngroups > h->split_max_groups) return 1;
   const int K = h->cfg.navg, teams = h->geo.teams;
   const int64_t ctas = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
   int best = 1;
@@ -275,6 +283,18 @@ int ensure_split_buffers(const crn_handle *h, SplitBuf &b, int64_t ngroups, int 
   }
   return CRN_OK;
 }
+void free_staging(crn_handle *h) {
+  for (int i = 0; i < 2; i++) {
+    cudaFreeHost(h->h_stage[i]);
+    cudaFree(h->d_stage[i]);
+    h->h_stage[i] = h->d_stage[i] = nullptr;
+    free_results(h->stage_res[i]);
+    if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
+    if (h->stage_copied[i]) cudaEventDestroy(h->stage_copied[i]);
+    h->stage_done[i] = h->stage_copied[i] = nullptr;
+  }
+  h->chunk_groups = 0;
+}
 void free_split_buffers(SplitBuf &b) {
   cudaFree(b.d_scratch);
   cudaFree(b.d_gcount);
@@ -289,8 +309,9 @@ int shape_launch(crn_handle *h, crn::SenseParams &p, int64_t ngroups, SplitBuf &
   p.scratch = nullptr;
   p.gcount = nullptr;
   if (p.split > 1) {
-    int st = ensure_split_buffers(h, buf, ngroups, p.split);
-    if (st != CRN_OK) return st;
+    // preallocated at crn_create (pick_split never splits a batch larger than split_max_groups)
+    if ((size_t)ngroups * p.split * h->cfg.nsegs > buf.scratch_cap || (size_t)ngroups > buf.gcount_cap)
+      return crn::fail(CRN_ERR_INVALID, "split scratch too small for %lld groups x %d", (long long)ngroups, p.split);
     p.scratch = buf.d_scratch;
     p.gcount = buf.d_gcount;
   }
@@ -314,8 +335,16 @@ int launch(crn_handle *h, SplitBuf &split, const void *d_iq, int64_t ngroups, fl
   int grid = 1;
   int st = shape_launch(h, p, ngroups, split, &grid);
   if (st != CRN_OK) return st;
+  const bool shared_scratch = (p.split > 1) && (&split == &h->dev_split);
+  if (shared_scratch && h->dev_split_used && h->dev_split_stream != s)
+    CRN_CUDA(cudaStreamWaitEvent(s, h->dev_split_event, 0));  // the other stream's split launch owns the counters
   st = h->launch(p, h->cfg.window, h->cfg.detector, grid, s, nullptr);
   if (st == CRN_OK) h->launches++;
+  if (st == CRN_OK && shared_scratch) {
+    CRN_CUDA(cudaEventRecord(h->dev_split_event, s));
+    h->dev_split_stream = s;
+    h->dev_split_used = true;
+  }
   return st;
 }
 
@@ -452,6 +481,16 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
 
   CRN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CRN_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  // split scratch of the two batch paths, sized once: splitting only pays while a batch leaves CTAs idle, so batches
+  // beyond two full grids are never split
+  h->split_max_groups = 2 * (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
+  if (b.upg == 0) {
+    st = ensure_split_buffers(h, h->dev_split, h->split_max_groups, h->max_split);
+    if (st != CRN_OK) return st;
+    st = ensure_split_buffers(h, h->host_split, h->split_max_groups, h->max_split);
+    if (st != CRN_OK) return st;
+  }
+  CRN_CUDA(cudaEventCreateWithFlags(&h->dev_split_event, cudaEventDisableTiming));
 
   // streaming ring: ring_slots decisions of K frames each
   const size_t slot_bytes = h->sample_bytes * (size_t)cfg->navg * cfg->frame_len;
@@ -487,13 +526,8 @@ int crn_destroy(crn_handle *h) {
     free_split_buffers(s.split);
     if (s.done) cudaEventDestroy(s.done);
   }
-  for (int i = 0; i < 2; i++) {
-    cudaFreeHost(h->h_stage[i]);
-    cudaFree(h->d_stage[i]);
-    free_results(h->stage_res[i]);
-    if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
-    if (h->stage_copied[i]) cudaEventDestroy(h->stage_copied[i]);
-  }
+  free_staging(h);
+  if (h->dev_split_event) cudaEventDestroy(h->dev_split_event);
   cudaFree(h->d_tw);
   cudaFree(h->d_win);
   free_split_buffers(h->host_split);
@@ -510,6 +544,8 @@ int crn_ring_acquire(crn_handle *h, void **slot) {
   if (!h || !slot) return crn::fail(CRN_ERR_INVALID, "crn_ring_acquire: null argument");
   RingSlot &s = h->ring[h->fill_slot];
   if (s.state != 0) return crn::fail(CRN_ERR_OVERRUN, "ring full: %d decisions unread", h->inflight);
+  if (h->fill_frames >= h->cfg.navg)  // cannot happen through this API (crn_submit rolls back on failure); never hand out
+    return crn::fail(CRN_ERR_INVALID, "crn_ring_acquire: slot already holds %d frames", h->fill_frames);  // memory past the slot
   *slot = s.h_iq + h->sample_bytes * (size_t)h->fill_frames * h->cfg.frame_len;
   return CRN_OK;
 }
@@ -521,10 +557,14 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   RingSlot &s = h->ring[h->fill_slot];
   if (s.state != 0) return crn::fail(CRN_ERR_OVERRUN, "ring full: %d decisions unread", h->inflight);
   if (h->fill_frames == 0) s.first_frame = h->frames_seen;
-  h->fill_frames += nframes;
-  h->frames_seen += (uint64_t)nframes;
-  if (h->fill_frames < h->cfg.navg) return CRN_OK;
-  // K-th frame: ship the slot and enqueue the fused kernel (stream ordered, non blocking)
+  if (h->fill_frames + nframes < h->cfg.navg) {
+    h->fill_frames += nframes;
+    h->frames_seen += (uint64_t)nframes;
+    return CRN_OK;
+  }
+  // K-th frame: ship the slot and enqueue the fused kernel (stream ordered, non blocking).  The frame counters are
+  // committed only once the launch is queued: a CUDA failure leaves the slot as it was before this call, so the next
+  // crn_ring_acquire stays inside the slot (the caller resubmits or calls crn_reset).
   CRN_CUDA(cudaSetDevice(h->device));
   const size_t slot_bytes = h->sample_bytes * (size_t)h->cfg.navg * h->cfg.frame_len;
   crn::SenseParams p = h->base;
@@ -551,6 +591,7 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   if (st != CRN_OK) return st;
   h->launches++;
   CRN_CUDA(cudaEventRecord(s.done, h->stream));
+  h->frames_seen += (uint64_t)nframes;
   s.state = 1;
   h->inflight++;
   h->fill_slot = (h->fill_slot + 1) % (int)h->ring.size();
@@ -606,15 +647,25 @@ int crn_sense_batch_host(crn_handle *h, const void *iq_, int64_t ngroups, crn_re
     // ~64 MiB chunks: large enough to amortise launch + copy latency, small enough to overlap
     int64_t cg = (int64_t)((64u << 20) / group_bytes);
     if (cg < 1) cg = 1;
-    h->chunk_groups = cg;
-    for (int i = 0; i < 2; i++) {
-      CRN_CUDA(cudaMallocHost(&h->h_stage[i], cg * group_bytes));
-      CRN_CUDA(cudaMalloc(&h->d_stage[i], cg * group_bytes));
-      int st = alloc_results(h->stage_res[i], cg, h->cfg.nbands);
-      if (st != CRN_OK) return st;
-      CRN_CUDA(cudaEventCreateWithFlags(&h->stage_done[i], cudaEventDisableTiming));
-      CRN_CUDA(cudaEventCreateWithFlags(&h->stage_copied[i], cudaEventDisableTiming));
+    // chunk_groups is set only when every staging buffer exists; a failure part-way releases what was allocated, so
+    // the next call starts over instead of running on null buffers
+    auto stage_alloc = [&]() -> int {
+      for (int i = 0; i < 2; i++) {
+        CRN_CUDA(cudaMallocHost(&h->h_stage[i], cg * group_bytes));
+        CRN_CUDA(cudaMalloc(&h->d_stage[i], cg * group_bytes));
+        int st = alloc_results(h->stage_res[i], cg, h->cfg.nbands);
+        if (st != CRN_OK) return st;
+        CRN_CUDA(cudaEventCreateWithFlags(&h->stage_done[i], cudaEventDisableTiming));
+        CRN_CUDA(cudaEventCreateWithFlags(&h->stage_copied[i], cudaEventDisableTiming));
+      }
+      return CRN_OK;
+    };
+    const int ast = stage_alloc();
+    if (ast != CRN_OK) {
+      free_staging(h);
+      return ast;
     }
+    h->chunk_groups = cg;
   }
   // Is the caller's buffer already page-locked?  Then DMA straight from it.
   cudaPointerAttributes pa;

@@ -74,6 +74,7 @@ CE_Predictive_Node::CE_Predictive_Node(int argc, char **argv, ExtensibleCognitiv
     cfg.postop = CRN_POST_SQUARE_OF_SUM;
   }
   cfg.device = device;
+  custom_weights = weights_path != NULL;
   if (weights_path && load_weights(weights_path) < 0) exit(EXIT_FAILURE);  // the reference's error convention
   if (log_path) result_log = fopen(log_path, "wb");
 }
@@ -113,6 +114,17 @@ bad:
   return -1;
 }
 
+// Receiver-side hook (ExtensibleCognitiveRadio::set_rx_slot_provider): where the next packet should be received.
+// Runs on the rx thread with CE_mutex held, i.e. never concurrently with execute().
+std::complex<float> *CE_Predictive_Node::rx_slot(void *self, size_t nsamples, int *overflow) {
+  CE_Predictive_Node *ce = (CE_Predictive_Node *)self;
+  void *slot = NULL;
+  if (!ce->sense || (int)nsamples != ce->cfg.frame_len) return NULL;
+  const int st = crn_ring_acquire(ce->sense, &slot);
+  if (st == CRN_ERR_OVERRUN && overflow) *overflow = 1;
+  return st == CRN_OK ? (std::complex<float> *)slot : NULL;
+}
+
 CE_Predictive_Node::~CE_Predictive_Node() {
   if (sense) crn_destroy(sense);
   if (result_log) fclose(result_log);
@@ -135,6 +147,14 @@ void CE_Predictive_Node::execute() {
       exit(EXIT_FAILURE);
     }
     config = 1;
+#ifdef CRN_ECR_HAS_RX_SLOT_PROVIDER
+    // from now on the receiver may recv() straight into the pinned ring (no memcpy here or under CE_mutex)
+    ECR->set_rx_slot_provider(&CE_Predictive_Node::rx_slot, this);
+#endif
+    if (!quiet && (cfg.nfft != 512 || cfg.detector != CRN_DET_MAG || cfg.postop != CRN_POST_SQUARE_OF_SUM ||
+                   cfg.window != CRN_WINDOW_RECT) && !custom_weights)
+      printf("CE_Predictive_Node: note: the built-in MLP literals (.cpp:78-120) were trained on (sum|X|)^2 features of "
+             "the 512-point rectangular mode; with -n/-w/-p changed, supply retrained weights with -m\n");
   }
 
   // sensing gate (.cpp:127-141), including upstream's habit of not carrying microseconds into seconds
@@ -153,7 +173,9 @@ void CE_Predictive_Node::execute() {
     void *slot = NULL;
     int st = crn_ring_acquire(sense, &slot);
     if (st == CRN_OK) {
-      memcpy(slot, ECR->ce_usrp_rx_buffer, (size_t)ECR->ce_usrp_rx_buffer_length * sizeof(float) * 2);
+      // the receiver may already have put the packet where it belongs (rx_slot below); otherwise copy it (.cpp:149)
+      if ((void *)ECR->ce_usrp_rx_buffer != slot)
+        memmove(slot, ECR->ce_usrp_rx_buffer, (size_t)ECR->ce_usrp_rx_buffer_length * sizeof(float) * 2);
       st = crn_submit(sense, 1);
     }
     if (st != CRN_OK) {

@@ -8,6 +8,7 @@
 
 #include <sys/time.h>
 
+#include <complex>
 #include <vector>
 
 #include "cognitive_engine.hpp"
@@ -30,12 +31,15 @@ private:
   int config;
   int fft_counter;
   int quiet;
+  bool custom_weights;
 
   crn_config cfg;
   crn_handle *sense;
   FILE *result_log;
 
   int load_weights(const char *path);  // -m <file>: the reference's `WeightIH[i][j] = v;` syntax
+  // receiver hook: the pinned ring slot the next packet should be received into (see extensible_cognitive_radio.hpp)
+  static std::complex<float> *rx_slot(void *self, size_t nsamples, int *overflow);
 
 public:
   CE_Predictive_Node(int argc, char **argv, ExtensibleCognitiveRadio *_ECR);

@@ -55,7 +55,8 @@ public:
 // Flat little-endian complex64 file (what the synthetic generator and any SDR recorder write).
 class FileIqSource : public IqSource {
 public:
-  explicit FileIqSource(const std::string &path, bool loop = false);
+  // loop: start over at the end of the file; max_packets > 0 ends a looped replay after that many packets
+  explicit FileIqSource(const std::string &path, bool loop = false, long max_packets = 0);
   ~FileIqSource();
   bool ok() const { return fp_ != nullptr; }
   size_t recv(std::complex<float> *buf, size_t max_samps) override;
@@ -63,6 +64,7 @@ public:
 private:
   void *fp_;
   bool loop_;
+  long left_;
 };
 
 class ExtensibleCognitiveRadio {
@@ -93,6 +95,19 @@ public:
   std::complex<float> *ce_usrp_rx_buffer;
   int ce_usrp_rx_buffer_length;
 
+  // --- direct-to-slot receive (the "RX buffer handoff" change to cpp:1310-1324) ---
+  // An engine that stages packets in memory of its own (libcrnsense's pinned ring) can ask the receiver to recv()
+  // STRAIGHT into it: while sensing is armed and no handoff is pending, the rx worker calls the provider under
+  // CE_mutex (so it never runs concurrently with execute()) for the address the next packet of `nsamples` samples
+  // should land in, receives there, and hands it over by pointing ce_usrp_rx_buffer at it - no memcpy under the
+  // mutex, and none in the engine.  The provider returns NULL to decline (the packet then takes the usual
+  // rx_buffer -> ce_usrp_rx_buffer copy); if it also sets *overflow the receiver raises UHD_OVERFLOW on the CE
+  // (cpp:1327-1336: what upstream does when the USRP reports an overflow).  Engines that never register one -
+  // every unmodified reference engine - see ce_usrp_rx_buffer exactly as before.
+#define CRN_ECR_HAS_RX_SLOT_PROVIDER 1
+  typedef std::complex<float> *(*rx_slot_provider)(void *ctx, size_t nsamples, int *overflow);
+  void set_rx_slot_provider(rx_slot_provider fn, void *ctx);
+
   // --- radio parameters: stored, reported back, counted; no hardware behind them ---
   void set_tx_freq(double f);
   void set_tx_rate(double r);
@@ -115,6 +130,12 @@ public:
   // --- replay specific ---
   void set_iq_source(IqSource *src, int packet_len);  // packet_len = get_max_recv_samps_per_packet()
   void set_lockstep(bool on);
+  // Lock-step holds a packet until the engine has consumed the previous one AND armed sensing.  An engine that never
+  // senses (CE_Template, the PU engines) would hold the receiver forever, so until sensing has been armed at least
+  // once the wait is bounded by this patience (default 1000 ms of wall clock - ten of the reference engine's 100 ms
+  // re-arm periods); after it expires packets are dropped while sensing is off, as upstream does (cpp:1310).
+  void set_lockstep_patience_ms(double ms);
+  unsigned long packets_direct() const { return direct_; }   // packets received straight into an engine slot
   void wait_for_end_of_capture();  // returns when the source is exhausted and the CE drained it
   unsigned long packets_received() const { return packets_; }
   unsigned long packets_forwarded() const { return forwarded_; }
@@ -135,6 +156,13 @@ private:
   bool capture_done;
   bool lockstep_, handoff_pending_;
   bool ce_ever_started_;  // lock-step replay: the rx worker holds the first packet until start_ce() has been called
+  std::atomic<bool> ever_sensed_;   // set_ce_sensing(1) has been called at least once
+  bool patience_spent_;             // lock-step: the bounded wait for a never-sensing engine has expired once
+  double lockstep_patience_ms_;
+  rx_slot_provider slot_fn_;
+  void *slot_ctx_;
+  std::complex<float> *ce_buffer_own_;  // the buffer ce_usrp_rx_buffer points at when a packet is copied (cpp:1269)
+  unsigned long direct_;
   IqSource *src_;
   std::complex<float> *rx_buffer;
   size_t rx_buffer_len;
@@ -142,6 +170,7 @@ private:
   bool tx_on_;
   unsigned long packets_, forwarded_, tx_retunes_, executions_;
   friend void *ECR_rx_worker(void *);
+  friend void ECR_lockstep_gate(ExtensibleCognitiveRadio *);
   friend void *ECR_ce_worker(void *);
 };
 

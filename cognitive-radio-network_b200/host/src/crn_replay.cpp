@@ -19,12 +19,15 @@
 int main(int argc, char **argv) {
   std::string scenario, iq, ce_args_override;
   int node = 2, packet_len = 512;
-  bool lockstep = true, have_override = false;
+  bool lockstep = true, have_override = false, loop = false;
+  double patience_ms = -1.0;
+  long max_packets = 0;
   static struct option opts[] = {{"scenario", 1, 0, 's'}, {"node", 1, 0, 'n'},       {"iq", 1, 0, 'i'},
                                  {"packet-len", 1, 0, 'l'}, {"ce-args", 1, 0, 'a'}, {"free-run", 0, 0, 'f'},
+                                 {"lockstep-patience-ms", 1, 0, 'p'}, {"repeat-packets", 1, 0, 'r'},
                                  {0, 0, 0, 0}};
   int o;
-  while ((o = getopt_long(argc, argv, "s:n:i:l:a:f", opts, NULL)) != -1) {
+  while ((o = getopt_long(argc, argv, "s:n:i:l:a:fp:r:", opts, NULL)) != -1) {
     switch (o) {
       case 's': scenario = optarg; break;
       case 'n': node = atoi(optarg); break;
@@ -32,8 +35,11 @@ int main(int argc, char **argv) {
       case 'l': packet_len = atoi(optarg); break;
       case 'a': ce_args_override = optarg; have_override = true; break;
       case 'f': lockstep = false; break;
+      case 'p': patience_ms = atof(optarg); break;
+      case 'r': max_packets = atol(optarg); loop = true; break;  // replay the capture in a loop for this many packets
       default:
-        fprintf(stderr, "usage: %s --scenario file.cfg --node N --iq capture.c64 [--packet-len L] [--ce-args \"...\"] [--free-run]\n", argv[0]);
+        fprintf(stderr, "usage: %s --scenario file.cfg --node N --iq capture.c64 [--packet-len L] [--ce-args \"...\"] [--free-run] "
+                        "[--lockstep-patience-ms MS] [--repeat-packets N]\n", argv[0]);
         return 2;
     }
   }
@@ -54,7 +60,7 @@ int main(int argc, char **argv) {
   }
   if (have_override) np.ce_args = ce_args_override;
 
-  FileIqSource src(iq);
+  FileIqSource src(iq, loop, max_packets);
   if (!src.ok()) {
     fprintf(stderr, "crn_replay: cannot open IQ capture %s\n", iq.c_str());
     return 1;
@@ -76,15 +82,22 @@ int main(int argc, char **argv) {
   ECR->set_ce((char *)np.cognitive_engine.c_str(), ce_argc, ce_argv);
   ECR->set_iq_source(&src, packet_len);
   ECR->set_lockstep(lockstep);
+  if (patience_ms >= 0.0) ECR->set_lockstep_patience_ms(patience_ms);
 
+  struct timeval t0, t1;
+  gettimeofday(&t0, NULL);
   ECR->start_rx();
   ECR->start_ce();
   ECR->wait_for_end_of_capture();
+  gettimeofday(&t1, NULL);
   ECR->stop_ce();
+  const double secs = (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_usec - t0.tv_usec);
   printf("crn_replay: node%d engine=%s rx=%.0f Hz @ %.0f S/s: %lu packets received, %lu forwarded to the CE, "
          "%lu CE executions, final tx_freq=%.0f Hz\n",
          node, np.cognitive_engine.c_str(), ECR->get_rx_freq(), ECR->get_rx_rate(), ECR->packets_received(),
          ECR->packets_forwarded(), ECR->ce_executions(), ECR->get_tx_freq());
+  printf("crn_replay: %lu packets received straight into engine slots (no copy), %.3f s, %.2f us per forwarded packet\n",
+         ECR->packets_direct(), secs, ECR->packets_forwarded() ? 1e6 * secs / (double)ECR->packets_forwarded() : 0.0);
   delete ECR;
   return 0;
 }

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <time.h>
 
 
 void *ECR_rx_worker(void *arg);
@@ -17,26 +18,32 @@ void *ECR_ce_worker(void *arg);
 CognitiveEngine *crn_create_ce(const char *name, int argc, char **argv, ExtensibleCognitiveRadio *ecr);
 
 // ---- file source ------------------------------------------------------------------------------------
-FileIqSource::FileIqSource(const std::string &path, bool loop) : fp_(fopen(path.c_str(), "rb")), loop_(loop) {}
+FileIqSource::FileIqSource(const std::string &path, bool loop, long max_packets)
+    : fp_(fopen(path.c_str(), "rb")), loop_(loop), left_(max_packets) {}
 FileIqSource::~FileIqSource() {
   if (fp_) fclose((FILE *)fp_);
 }
 size_t FileIqSource::recv(std::complex<float> *buf, size_t max_samps) {
   if (!fp_) return 0;
+  if (left_ < 0) return 0;  // a looped replay delivered its max_packets
   size_t n = fread(buf, sizeof(std::complex<float>), max_samps, (FILE *)fp_);
   if (n < max_samps && loop_) {
     rewind((FILE *)fp_);
     n += fread(buf + n, sizeof(std::complex<float>), max_samps - n, (FILE *)fp_);
   }
   // a trailing partial packet is dropped: upstream always hands over full rx_buffer_len packets
-  return n == max_samps ? n : 0;
+  if (n != max_samps) return 0;
+  if (left_ > 0 && --left_ == 0) left_ = -1;
+  return n;
 }
 
 // ---- radio ------------------------------------------------------------------------------------------
 ExtensibleCognitiveRadio::ExtensibleCognitiveRadio()
     : ce_usrp_rx_buffer(nullptr), ce_usrp_rx_buffer_length(0), CE(nullptr), ce_timeout_ms(1000.0),
       ce_sensing_flag(0), ce_thread_running(true), ce_running(false), rx_thread_running(true),
-      rx_running(false), capture_done(false), lockstep_(false), handoff_pending_(false), ce_ever_started_(false), src_(nullptr),
+      rx_running(false), capture_done(false), lockstep_(false), handoff_pending_(false), ce_ever_started_(false), ever_sensed_(false),
+      patience_spent_(false), lockstep_patience_ms_(1000.0), slot_fn_(nullptr), slot_ctx_(nullptr), ce_buffer_own_(nullptr),
+      direct_(0), src_(nullptr),
       rx_buffer(nullptr), rx_buffer_len(0), tx_freq_(460e6), tx_rate_(1e6), tx_gain_soft_(-12.0),
       tx_gain_uhd_(0.0), rx_freq_(460e6), rx_rate_(1e6), rx_gain_uhd_(0.0), tx_on_(false), packets_(0),
       forwarded_(0), tx_retunes_(0), executions_(0) {
@@ -69,7 +76,7 @@ ExtensibleCognitiveRadio::~ExtensibleCognitiveRadio() {
   pthread_join(rx_process, NULL);
   pthread_join(CE_process, NULL);
   free(rx_buffer);
-  free(ce_usrp_rx_buffer);
+  free(ce_buffer_own_);
 }
 
 void ExtensibleCognitiveRadio::set_ce(char *ce, int argc, char **argv) {
@@ -95,7 +102,16 @@ void ExtensibleCognitiveRadio::stop_ce() {
 }
 void ExtensibleCognitiveRadio::set_ce_timeout_ms(double t) { ce_timeout_ms = t; }
 double ExtensibleCognitiveRadio::get_ce_timeout_ms() { return ce_timeout_ms; }
-void ExtensibleCognitiveRadio::set_ce_sensing(int on) { ce_sensing_flag = on; }  // no lock, as upstream (cpp:389-391)
+void ExtensibleCognitiveRadio::set_ce_sensing(int on) {  // no lock, as upstream (cpp:389-391)
+  if (on) ever_sensed_ = true;
+  ce_sensing_flag = on;
+}
+// called from the engine (CE thread, CE_mutex held) or before start_ce()
+void ExtensibleCognitiveRadio::set_rx_slot_provider(rx_slot_provider fn, void *ctx) {
+  slot_fn_ = fn;
+  slot_ctx_ = ctx;
+}
+void ExtensibleCognitiveRadio::set_lockstep_patience_ms(double ms) { lockstep_patience_ms_ = ms; }
 
 #define LOCKED(m, stmt)        \
   do {                         \
@@ -136,9 +152,10 @@ void ExtensibleCognitiveRadio::set_iq_source(IqSource *src, int packet_len) {
   rx_buffer_len = (size_t)packet_len;
   ce_usrp_rx_buffer_length = packet_len;
   free(rx_buffer);
-  free(ce_usrp_rx_buffer);
+  free(ce_buffer_own_);
   rx_buffer = (std::complex<float> *)malloc(rx_buffer_len * sizeof(std::complex<float>));
-  ce_usrp_rx_buffer = (std::complex<float> *)malloc(rx_buffer_len * sizeof(std::complex<float>));
+  ce_buffer_own_ = (std::complex<float> *)malloc(rx_buffer_len * sizeof(std::complex<float>));
+  ce_usrp_rx_buffer = ce_buffer_own_;
   capture_done = false;
   pthread_mutex_unlock(&rx_params_mutex);
 }
@@ -150,6 +167,28 @@ void ExtensibleCognitiveRadio::wait_for_end_of_capture() {
   pthread_mutex_unlock(&CE_mutex);
 }
 
+// Lock-step gate (CE_mutex held): wait until the engine took the previous packet and (re-)armed sensing.  start_rx()
+// precedes start_ce() (src/crts_cognitive_radio.cpp:810-812), so "CE not started YET" must wait as well - or a short
+// capture is drained before the engine ever runs; a CE that was stopped again lets packets drop.  An engine that has
+// never armed sensing is waited for at most lockstep_patience_ms_, once; after that only the consumption of the
+// previous event is awaited.
+void ECR_lockstep_gate(ExtensibleCognitiveRadio *ECR) {
+  struct timespec until;
+  clock_gettime(CLOCK_REALTIME, &until);
+  const double ns = (double)until.tv_nsec + ECR->lockstep_patience_ms_ * 1e6;
+  until.tv_sec += (time_t)(ns / 1e9);
+  until.tv_nsec = (long)fmod(ns, 1e9);
+  while (ECR->ce_thread_running && (ECR->ce_running || !ECR->ce_ever_started_)) {
+    const bool wait_for_arming = !ECR->ce_sensing_flag && (ECR->ever_sensed_ || !ECR->patience_spent_);
+    if (!ECR->handoff_pending_ && !wait_for_arming) break;
+    if (ECR->handoff_pending_ || ECR->ever_sensed_) {
+      pthread_cond_wait(&ECR->consumed_sig, &ECR->CE_mutex);
+    } else if (pthread_cond_timedwait(&ECR->consumed_sig, &ECR->CE_mutex, &until) == ETIMEDOUT) {
+      ECR->patience_spent_ = true;  // this engine does not sense: stop holding packets for it
+    }
+  }
+}
+
 // receiver worker: recv one packet, hand it to the CE when sensing is on (cpp:1258-1324)
 void *ECR_rx_worker(void *arg) {
   ExtensibleCognitiveRadio *ECR = (ExtensibleCognitiveRadio *)arg;
@@ -159,10 +198,34 @@ void *ECR_rx_worker(void *arg) {
     pthread_mutex_unlock(&ECR->rx_params_mutex);
     if (!ECR->rx_thread_running) break;
 
-    size_t n = ECR->src_->recv(ECR->rx_buffer, ECR->rx_buffer_len);
+    // where this packet lands: an engine slot (direct) when the engine offers one and is ready for it, else rx_buffer
+    std::complex<float> *dst = ECR->rx_buffer;
+    bool direct = false, gated = false;
+    if (ECR->slot_fn_ && (ECR->ce_sensing_flag || ECR->lockstep_)) {
+      pthread_mutex_lock(&ECR->CE_mutex);
+      if (ECR->lockstep_) {
+        ECR_lockstep_gate(ECR);
+        gated = true;
+      }
+      if (ECR->slot_fn_ && ECR->ce_sensing_flag && !ECR->handoff_pending_) {
+        int overflow = 0;
+        std::complex<float> *p = ECR->slot_fn_(ECR->slot_ctx_, ECR->rx_buffer_len, &overflow);
+        if (p) {
+          dst = p;
+          direct = true;
+        } else if (overflow) {  // the consumer's ring is full: tell the engine as upstream reports a USRP overflow
+          ECR->CE_metrics.CE_event = ExtensibleCognitiveRadio::UHD_OVERFLOW;
+          ECR->handoff_pending_ = true;
+          pthread_cond_signal(&ECR->CE_execute_sig);
+        }
+      }
+      pthread_mutex_unlock(&ECR->CE_mutex);
+    }
+
+    size_t n = ECR->src_->recv(dst, ECR->rx_buffer_len);
     if (n == 0) {  // end of capture: let the engine finish, then report
       pthread_mutex_lock(&ECR->CE_mutex);
-      while (ECR->lockstep_ && ECR->handoff_pending_ && ECR->ce_thread_running)
+      while (ECR->lockstep_ && ECR->handoff_pending_ && ECR->ce_thread_running && ECR->ce_running)
         pthread_cond_wait(&ECR->consumed_sig, &ECR->CE_mutex);
       ECR->capture_done = true;
       pthread_cond_broadcast(&ECR->done_sig);
@@ -176,16 +239,15 @@ void *ECR_rx_worker(void *arg) {
 
     if (ECR->ce_sensing_flag || ECR->lockstep_) {
       pthread_mutex_lock(&ECR->CE_mutex);
-      if (ECR->lockstep_) {
-        // wait until the engine took the previous packet and (re-)armed sensing.  start_rx() precedes
-        // start_ce() (src/crts_cognitive_radio.cpp:810-812), so "CE not started YET" must wait as well - or a
-        // short capture is drained before the engine ever runs; a CE that was stopped again lets packets drop.
-        while ((ECR->handoff_pending_ || !ECR->ce_sensing_flag) && ECR->ce_thread_running &&
-               (ECR->ce_running || !ECR->ce_ever_started_))
-          pthread_cond_wait(&ECR->consumed_sig, &ECR->CE_mutex);
-      }
+      if (ECR->lockstep_ && !gated) ECR_lockstep_gate(ECR);
       if (ECR->ce_sensing_flag) {  // re-check under the mutex, as upstream does (cpp:1313)
-        memcpy(ECR->ce_usrp_rx_buffer, ECR->rx_buffer, ECR->rx_buffer_len * sizeof(std::complex<float>));
+        if (direct) {
+          ECR->ce_usrp_rx_buffer = dst;  // already in the engine's slot
+          ECR->direct_++;
+        } else {
+          ECR->ce_usrp_rx_buffer = ECR->ce_buffer_own_;
+          memcpy(ECR->ce_buffer_own_, ECR->rx_buffer, ECR->rx_buffer_len * sizeof(std::complex<float>));
+        }
         ECR->CE_metrics.CE_event = ExtensibleCognitiveRadio::USRP_RX_SAMPS;
         ECR->handoff_pending_ = true;
         ECR->forwarded_++;

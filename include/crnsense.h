@@ -181,8 +181,10 @@ int crn_sense_batch_host(crn_handle *h, const void *iq, int64_t ngroups, crn_res
    bits, every time.  Launches of different shapes (one 300-group batch vs chunks of 128, the one-decision
    launches of the streaming path) may deal a group's frames to a different number of CTAs, which re-associates
    the fp32 band sums: such results agree to fp32 rounding (~1e-7 relative), far inside the 1e-4 parity bar.
-   Consecutive crn_sense_batch_device calls on one handle share scratch memory and must be stream-ordered with
-   respect to each other (one handle per stream); the streaming ring and crn_sense_batch_host have their own. */
+   The call never allocates and never synchronises (scratch for split launches is sized at crn_create), so it may be
+   captured into a CUDA graph.  Launches of one handle on DIFFERENT streams are safe: the few-group launches that
+   share the handle's scratch are chained with an event (the later one waits for the earlier); large batches run
+   concurrently.  A handle is still not thread-safe: call it from one host thread at a time. */
 int crn_sense_batch_device(crn_handle *h, const void *d_iq, int64_t ngroups, float *d_feat,
                            double *d_ann, int32_t *d_decision, uint64_t *d_mask, void *cuda_stream);
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, feat_close
+from conftest import GOLDEN, feat_close, feat_err
 
 pytestmark = pytest.mark.gpu
 
@@ -402,7 +402,9 @@ def test_full_size_parseval_and_sampled_parity(crn, oracle, torch):
     iq_s = np.concatenate([d_iq[g * gs:(g + 1) * gs].cpu().numpy().view(np.complex64).ravel() for g in pick])
     want = oracle.sense_port(cfg, iq_s, nthreads=8)
     got = (d_feat.cpu().numpy()[pick], d_ann.cpu().numpy()[pick], d_dec.cpu().numpy()[pick], None)
-    assert feat_close(got[0], want[0], FEAT_RTOL)
+    print("full size: max relative feature error (no floor) %.3g, max |ANN - oracle| %.3g over %d sampled groups"
+          % (feat_err(got[0], want[0]), np.abs(got[1] - want[1]).max(), len(pick)))
+    assert feat_err(got[0], want[0]) <= FEAT_RTOL   # every band, the 1e-5-of-channel noise floor included
     assert np.abs(got[1] - want[1]).max() <= ANN_ATOL
     assert np.array_equal(got[2], want[2])
     # the PU hops over all three channels during the capture and the MLP follows it
@@ -422,6 +424,43 @@ def test_full_size_parseval_and_sampled_parity(crn, oracle, torch):
         rhs[g0:g0 + blk.shape[0]] = ((blk ** 2).sum(dim=3) * win ** 2).sum(dim=(1, 2)) * (nfft / K)
     rel = ((lhs - rhs).abs() / rhs).max().item()
     assert rel <= 2e-5, rel
+
+
+@pytest.mark.parametrize("snr,hop", [(-5.0, 0), (0.0, 1), (5.0, 2), (20.0, 0), (10.0, 1), (10.0, 2)])
+def test_large_batch_across_snr_and_hop_models(crn, oracle, torch, snr, hop):
+    """BASELINE config 2 shape, 2000 decisions (131e6 samples, far more groups than CTAs) at the SNRs SURVEY 8d lists and
+    all three PU hop models (Markov as documented / as coded / uniform): 48 groups spread over the batch against the
+    oracle, relative feature error WITHOUT a tolerance floor (at -5 dB the bands are nearly equal, at +20 dB the noise
+    floor band is ~1e-3 of the occupied channel)."""
+    cfg = crn.config_welch(1024, 64)
+    gs = cfg.group_samples
+    ngroups = 2000
+    sc = crn.synth_config(gs, dwell_groups=16, snr_db=snr, seed=1000 + hop, hop_mode=hop)
+    d_iq = torch.empty(ngroups * gs, 2, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    crn.synth_generate(sc, d_iq, 0, ngroups * gs, None, 0, stream)
+    d_feat = torch.empty(ngroups, 4, dtype=torch.float32, device="cuda")
+    d_ann = torch.empty(ngroups, 3, dtype=torch.float64, device="cuda")
+    d_dec = torch.empty(ngroups, dtype=torch.int32, device="cuda")
+    with crn.Sensor(cfg, device=0) as s:
+        s.sense_device(d_iq, ngroups, d_feat, d_ann, d_dec, None, stream)
+    torch.cuda.synchronize()
+    pick = np.unique(np.linspace(0, ngroups - 1, 48).round().astype(int))
+    iq_s = d_iq.view(ngroups, gs, 2)[torch.from_numpy(pick).cuda()].cpu().numpy().view(np.complex64).ravel()
+    of, oa, od, _ = oracle.sense_port(cfg, iq_s, nthreads=8)
+    gf, ga, gd = d_feat.cpu().numpy()[pick], d_ann.cpu().numpy()[pick], d_dec.cpu().numpy()[pick]
+    err = feat_err(gf, of)
+    print("snr %+.0f dB hop %d: max relative feature error (no floor) %.3g, NF/max band %.2e, max |ANN - oracle| %.3g"
+          % (snr, hop, err, float((of[:, 0] / of.max(axis=1)).min()), np.abs(ga - oa).max()))
+    assert err <= FEAT_RTOL
+    # low SNR parks hidden units mid-sigmoid, where a 1e-7 feature difference is amplified: bound the MLP by what the
+    # feature difference explains (as `check` does), and require equal decisions away from the threshold
+    mlp_ann, mlp_dec = oracle.mlp_f64(cfg, gf)
+    assert np.abs(ga - mlp_ann).max() <= 1e-9 and np.array_equal(gd, mlp_dec)
+    tol = ANN_ATOL + 2 * np.abs(mlp_ann - oa).max(axis=1, keepdims=True)
+    assert np.all(np.abs(ga - oa) <= tol)
+    near = np.abs(oa - cfg.ann_threshold).min(axis=1) <= tol.ravel()
+    assert np.array_equal(gd[~near], od[~near])
 
 
 @pytest.mark.parametrize("nfft,mode,navg", [(512, "ref", 10), (1024, "welch", 64), (8192, "wide", 4), (2048, "welch", 7)])

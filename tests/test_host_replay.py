@@ -12,6 +12,7 @@ from conftest import GOLDEN, ROOT, feat_close
 HOST = os.path.join(ROOT, "cognitive-radio-network_b200", "host")
 REPLAY = os.path.join(HOST, "crn_replay")
 SCENARIO = os.path.join(GOLDEN, "predictive_model_su.cfg")
+REF_SCENARIO = os.path.join(GOLDEN, "reference_predictive_model.cfg")   # the reference's scenarios/predictive_model.cfg, unmodified
 
 
 @pytest.fixture(scope="module")
@@ -131,6 +132,55 @@ def test_reference_cpu_engine_on_this_radio_reproduces_the_fixtures(crn, tmp_pat
     assert "%d forwarded to the CE" % (10 * len(got)) in r.stdout
 
 
+@pytest.mark.skipif(not os.path.isdir(REF_ENGINES), reason="reference tree not present (GPU box)")
+def test_gpu_engine_compiles_against_the_reference_headers():
+    """Drop-in check in the other direction: the GPU-backed engine source, unmodified, against the REFERENCE's own
+    include/extensible_cognitive_radio.hpp and include/cognitive_engine.hpp (liquid / UHD type names from
+    oracle/compat, as for oracle O1), at the reference's language level (makefile:1, -std=c++11)."""
+    ref_inc = os.path.join(os.path.dirname(REF_ENGINES), "include")
+    src = os.path.join(HOST, "cognitive_engines", "CE_Predictive_Node", "CE_Predictive_Node.cpp")
+    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "oracle", "compat"),
+                        "-I" + ref_inc, "-I" + os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # and the scenario fixture below IS the reference's file
+    ref_cfg = os.path.join(os.path.dirname(REF_ENGINES), "scenarios", "predictive_model.cfg")
+    assert open(ref_cfg, "rb").read() == open(REF_SCENARIO, "rb").read()
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_scenario_runs_on_the_gpu_engine(crn, replay, tmp_path):
+    """The reference's scenarios/predictive_model.cfg, byte for byte (tests/golden/reference_predictive_model.cfg, a
+    reference-held fixture), node 2: scenario reader -> radio setters -> rx/CE workers -> CE_Predictive_Node ->
+    libcrnsense, against the reference engine's results on the ragged-frame capture."""
+    g = np.load(os.path.join(GOLDEN, "ref_markov_L363.npz"))
+    iq = tmp_path / "cap.c64"
+    g["iq"].astype(np.complex64).tofile(iq)
+    log = tmp_path / "dec.bin"
+    r = run(replay, ["--scenario", REF_SCENARIO, "--node", "2", "--iq", str(iq), "--packet-len", "363",
+                     "--ce-args", "-d 0 -q -o %s" % log])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "engine=CE_Predictive_Node" in r.stdout
+    nd = len(g["decision"])
+    assert "%d packets received, %d forwarded" % (10 * nd, 10 * nd) in r.stdout
+    res = (crn.Result * nd).from_buffer_copy(open(log, "rb").read())
+    feat, ann, dec, _ = crn.results_to_arrays(res, 4)
+    assert feat_close(feat, g["feat"], 1e-4)
+    assert np.abs(ann - g["ann"]).max() <= 1e-5
+    assert np.array_equal(dec, g["decision"])
+
+
+def test_unmodified_reference_scenario_parses(replay, tmp_path):
+    """Without a GPU the same file must get as far as crn_create (and fail there loudly): every key of both node blocks
+    is accepted by the reader."""
+    iq = tmp_path / "z.c64"
+    np.zeros(512 * 10, np.complex64).tofile(iq)
+    r = run(replay, ["--scenario", REF_SCENARIO, "--node", "2", "--iq", str(iq), "--packet-len", "512"])
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode != 0 and "crn_create" in (r.stdout + r.stderr)
+    assert "parse error" not in (r.stdout + r.stderr).lower()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["ref_markov_L512", "ref_markov_L363", "ref_tone70"])
 def test_replayed_capture_matches_reference_engine_fixtures(crn, replay, tmp_path, case):
@@ -243,3 +293,44 @@ def test_registration_generator_scans_like_upstream(replay, tmp_path):
     assert srcs == [str(a / "CE_Alpha" / "CE_Alpha.cpp"), str(a / "CE_Alpha" / "helper.c"),
                     str(b / "CE_Gamma" / "CE_Gamma.cpp")]
     assert subprocess.run([gen, "--bogus"], capture_output=True).returncode == 2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ENGINES), reason="reference tree not present (GPU box)")
+def test_lockstep_does_not_hang_on_engines_that_never_sense(crn, tmp_path):
+    """Lock-step is crn_replay's default; CE_Template never calls set_ce_sensing(1).  The receiver must not hold its
+    packets forever: after the bounded patience they are dropped while sensing is off, as upstream does
+    (src/extensible_cognitive_radio.cpp:1310), and the capture ends."""
+    exe = _make(tmp_path, "%s %s" % (os.path.join(HOST, "cognitive_engines"), REF_ENGINES))
+    cfg = tmp_path / "t.cfg"
+    cfg.write_text('node1 : { cognitive_engine = "CE_Template"; ce_timeout_ms = 0; ce_args = "-d 1"; rx_freq = 833e6; rx_rate = 13e6; };')
+    iq = tmp_path / "z.c64"
+    np.zeros(512 * 40, np.complex64).tofile(iq)
+    r = run(exe, ["--scenario", str(cfg), "--node", "1", "--iq", str(iq), "--packet-len", "512", "--lockstep-patience-ms", "200"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "40 packets received, 0 forwarded" in r.stdout
+
+
+@pytest.mark.gpu
+def test_receiver_writes_straight_into_the_pinned_ring(crn, replay, tmp_path):
+    """Direct-to-slot handoff (the change to src/extensible_cognitive_radio.cpp:1310-1324): with the GPU engine every
+    forwarded packet is received in place in libcrnsense's pinned ring - no rx_buffer -> ce_usrp_rx_buffer -> slot
+    copies - in lock-step and in free-run, and the decisions are the reference engine's."""
+    g = np.load(os.path.join(GOLDEN, "ref_markov_L512.npz"))
+    iq = tmp_path / "cap.c64"
+    g["iq"].astype(np.complex64).tofile(iq)
+    nd = len(g["decision"])
+    log = tmp_path / "dec.bin"
+    r = run(replay, ["--scenario", SCENARIO, "--node", "2", "--iq", str(iq), "--packet-len", "512", "--ce-args", "-d 0 -q -o %s" % log])
+    assert r.returncode == 0, r.stdout + r.stderr
+    # the first packet arrives before the engine has created its handle (the provider is registered in execute())
+    import re
+    direct = int(re.search(r"(\d+) packets received straight into engine slots", r.stdout).group(1))
+    assert 10 * nd - 2 <= direct <= 10 * nd, r.stdout
+    res = (crn.Result * nd).from_buffer_copy(open(log, "rb").read())
+    feat, ann, dec, _ = crn.results_to_arrays(res, 4)
+    assert feat_close(feat, g["feat"], 1e-4) and np.array_equal(dec, g["decision"])
+    # free-run: packets may be dropped (upstream semantics) but whatever is forwarded is still sensed in order
+    r = run(replay, ["--scenario", SCENARIO, "--node", "2", "--iq", str(iq), "--packet-len", "512", "--free-run",
+                     "--repeat-packets", "20000", "--ce-args", "-d 0 -q"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "20000 packets received" in r.stdout

@@ -212,3 +212,54 @@ def test_synth_interferer_waveforms(crn, oracle):
     f0 = oracle.sense_port(cfg, oracle.synth(cap, 4 * cfg.group_samples)[0])[0]
     f1 = oracle.sense_port(cfg, oracle.synth(jam, 4 * cfg.group_samples)[0])[0]
     assert (f1[:, 0] > 50 * f0[:, 0]).all() and np.allclose(f1[:, 1:], f0[:, 1:], rtol=0.05)
+
+
+def _cfg_fields(c):
+    return dict(nfft=c.nfft, frame_len=c.frame_len, frame_stride=c.frame_stride, navg=c.navg, window=c.window,
+                detector=c.detector, postop=c.postop, decide=c.decide, nbands=c.nbands, nsegs=c.nsegs,
+                segs=[(c.segs[i].band, c.segs[i].lo, c.segs[i].hi) for i in range(c.nsegs)],
+                wih=[[c.ann_wih[i][j] for j in range(6)] for i in range(5)],
+                who=[[c.ann_who[j][k] for k in range(4)] for j in range(6)],
+                thr=c.ann_threshold, ef=c.energy_factor, ring=c.ring_slots, fmt=c.iq_format)
+
+
+def test_oracle_configs_equal_the_product_fillers(crn, oracle):
+    """The oracle states the workloads on its own (oracle/crn_oracle_config.c, restated from the reference's literals
+    and loop bounds) so that bench.py's reference arm never loads the product library; the two statements must say
+    the same thing, field for field, and the struct mirrors must have the same layout."""
+    import ctypes as C
+    assert C.sizeof(oracle.Config) == C.sizeof(crn.Config) and C.sizeof(oracle.SynthConfig) == C.sizeof(crn.SynthConfig)
+    for name, _ in crn.Config._fields_:
+        assert getattr(oracle.Config, name).offset == getattr(crn.Config, name).offset, name
+    for name, _ in crn.SynthConfig._fields_:
+        assert getattr(oracle.SynthConfig, name).offset == getattr(crn.SynthConfig, name).offset, name
+    assert _cfg_fields(oracle.config_reference()) == _cfg_fields(crn.config_reference())
+    for nfft in (256, 512, 1024, 2048, 4096, 8192):
+        assert _cfg_fields(oracle.config_welch(nfft, 64)) == _cfg_fields(crn.config_welch(nfft, 64)), nfft
+        nch = 16 if nfft == 256 else 64
+        assert _cfg_fields(oracle.config_wideband(nfft, 7, nch)) == _cfg_fields(crn.config_wideband(nfft, 7, nch)), nfft
+    a, b = oracle.synth_config(65536, snr_db=3.0, hop_mode=2), crn.synth_config(65536, snr_db=3.0, hop_mode=2)
+    assert bytes(a) == bytes(b)
+
+
+def test_welch_band_plan_at_256_points(crn):
+    """N = 256 halves the reference's bin indices (bins are twice as wide); every segment stays non-empty, ordered and
+    inside the spectrum, and bin N-1 is still excluded from CH1 as upstream excludes 511 (.cpp:177)."""
+    c = crn.config_welch(256, 10)
+    assert crn.validate(c) == crn.OK
+    segs = [(c.segs[i].band, c.segs[i].lo, c.segs[i].hi) for i in range(c.nsegs)]
+    assert segs == [(0, 150, 155), (1, 0, 8), (1, 248, 255), (2, 27, 42), (3, 94, 111)]
+
+
+def test_reference_arm_never_loads_the_product_library():
+    """bench.py --impl reference in a fresh interpreter: its JSON line lists the shared objects of this repo it mapped."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["native_so_mapped"] and all(m.startswith("oracle/") for m in line["native_so_mapped"]), line["native_so_mapped"]
