@@ -296,8 +296,9 @@ class Ctx:
 def measure(ctx, name, steps, warmup, env=None, keep=False, parity_groups=64):
     """Device-resident timing of ONE workload on this rank's GPU (+ parity spot check against the oracle, outside the
     timed region).  A step = one fused launch over the rank's batch + the device->host read of its results
-    (features, MLP outputs, decisions, masks) into pinned memory: `first kernel launch to last feature readback`,
-    SURVEY 8d.  Returns a dict; with keep=True the tensors stay alive in it for the e2e leg."""
+    (features, MLP outputs, decisions, masks) into pinned memory; the timed region runs from the first kernel launch
+    to the last feature readback, the readback of step i overlapping the kernel of step i+1 (two result
+    sets, a copy stream).  Returns a dict; with keep=True the tensors stay alive in it for the e2e leg."""
     import numpy as np
     import torch
     crn, cdist, world, rank, local_rank, dev = ctx.crn, ctx.cdist, ctx.world, ctx.rank, ctx.local_rank, ctx.dev
@@ -333,43 +334,59 @@ def measure(ctx, name, steps, warmup, env=None, keep=False, parity_groups=64):
             d16[i0:i0 + step_q] = (d_iq[i0:i0 + step_q] * 32768.0).round_().clamp_(-32768, 32767).to(torch.int16)
         d_iq = d16
         torch.cuda.synchronize()
-    d_feat = torch.empty(ngroups, cfg.nbands, dtype=torch.float32, device=dev)
-    d_ann = torch.empty(ngroups, 3, dtype=torch.float64, device=dev)
-    d_dec = torch.empty(ngroups, dtype=torch.int32, device=dev)
-    d_mask = torch.empty(ngroups, dtype=torch.int64, device=dev)
-    h_res = [torch.empty_like(t, device="cpu").pin_memory() for t in (d_feat, d_ann, d_dec, d_mask)]
-    d2h_bytes = sum(t.numel() * t.element_size() for t in h_res)
+    # two result sets: the results of step i are read back (copy stream) while the kernel of step i+1 runs
+    def result_set():
+        return (torch.empty(ngroups, cfg.nbands, dtype=torch.float32, device=dev),
+                torch.empty(ngroups, 3, dtype=torch.float64, device=dev),
+                torch.empty(ngroups, dtype=torch.int32, device=dev),
+                torch.empty(ngroups, dtype=torch.int64, device=dev))
+    d_sets = [result_set(), result_set()]
+    h_sets = [[torch.empty_like(t, device="cpu").pin_memory() for t in d] for d in d_sets]
+    d2h_bytes = sum(t.numel() * t.element_size() for t in h_sets[0])
+    main_stream = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    copied = [None, None]   # event: this set's previous readback has finished
 
-    def step():
-        sensor.sense_device(d_iq, ngroups, d_feat, d_ann, d_dec, d_mask, stream)
+    def step(i, ev_kernel):
+        """fused launch of step i into result set i % 2, then its readback queued on the copy stream"""
+        b = i & 1
+        if copied[b] is not None:
+            main_stream.wait_event(copied[b])      # the set is free again (it was, long ago)
+        sensor.sense_device(d_iq, ngroups, d_sets[b][0], d_sets[b][1], d_sets[b][2], d_sets[b][3], stream)
+        ev_kernel.record(main_stream)
+        copy_stream.wait_event(ev_kernel)
+        with torch.cuda.stream(copy_stream):
+            for h, d in zip(h_sets[b], d_sets[b]):
+                h.copy_(d, non_blocking=True)
+            copied[b] = torch.cuda.Event()
+            copied[b].record(copy_stream)
 
-    def readback():
-        for h, d in zip(h_res, (d_feat, d_ann, d_dec, d_mask)):
-            h.copy_(d, non_blocking=True)
-
-    for _ in range(max(warmup, 3)):
-        step()
-        readback()
+    nwarm = max(warmup, 3)
+    for i in range(nwarm):
+        step(i, torch.cuda.Event())
     ctx.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25 if keep else 0.05)
     launches0 = sensor.launches
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
     ctx.barrier()
     t_wall0 = time.time()
-    ev[0].record()
+    ev[0].record(main_stream)
     for i in range(steps):
-        step()
-        ev[2 * i + 1].record()      # kernel done (roofline: launch duration)
-        readback()
-        ev[2 * i + 2].record()      # results in pinned host memory (value: to last feature readback)
+        step(nwarm + i, ev[i + 1])              # ev[i+1]: kernel i done; kernels run back to back on the main stream
+    main_stream.wait_event(copied[(nwarm + steps - 1) & 1])
+    main_stream.wait_event(copied[(nwarm + steps) & 1])
+    ev[steps + 1].record(main_stream)           # every result of every step is in pinned host memory
     ctx.barrier()
     t_wall1 = time.time()
     gpu_launches = sensor.launches - launches0
-    kern_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)]
-    total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    total_ms = ev[0].elapsed_time(ev[steps + 1])
+    last = (nwarm + steps - 1) & 1
+    d_feat, d_ann, d_dec, d_mask = d_sets[last]
+    h_res = h_sets[last]
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     total_ms_max = cdist.max_over_ranks(total_ms, dev)
     total_samples = (ngroups_all * gs) if strong else world * nsamp
@@ -406,7 +423,7 @@ def measure(ctx, name, steps, warmup, env=None, keep=False, parity_groups=64):
                             ngroups=ngroups, nsamp=nsamp, gs=gs, stream=stream)
     else:
         sensor.close()
-        del d_iq, d_feat, d_ann, d_dec, d_mask, d_state
+        del d_iq, d_feat, d_ann, d_dec, d_mask, d_state, d_sets
         torch.cuda.empty_cache()
     return out
 

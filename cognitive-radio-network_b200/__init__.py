@@ -146,6 +146,8 @@ API = {
     "crn_destroy": (C.c_int, [_P]),
     "crn_ring_acquire": (C.c_int, [_P, C.POINTER(_P)]),
     "crn_submit": (C.c_int, [_P, C.c_int32]),
+    "crn_create_many": (C.c_int, [C.POINTER(Config), C.c_int32, C.POINTER(_P)]),
+    "crn_submit_many": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32]),
     "crn_poll": (C.c_int, [_P, C.POINTER(Result)]),
     "crn_wait": (C.c_int, [_P, C.POINTER(Result)]),
     "crn_reset": (C.c_int, [_P]),
@@ -250,13 +252,38 @@ def _ptr(t):
 class Sensor:
     """One sensing stream on one GPU (the GPU-side state of a CE_Predictive_Node instance)."""
 
-    def __init__(self, cfg, device=None):
+    def __init__(self, cfg, device=None, _handle=None):
         self.cfg = cfg.copy()
         if device is not None:
             self.cfg.device = int(device)
+        if _handle is not None:   # a member of a crn_create_many pool
+            self._h = _handle
+            return
         h = _P()
         _check(lib.crn_create(C.byref(self.cfg), C.byref(h)), "crn_create")
         self._h = h
+
+    @classmethod
+    def create_many(cls, cfg, n, device=None):
+        """n streaming sensors of one configuration sharing one pinned ring (crn_create_many)."""
+        c = cfg.copy()
+        if device is not None:
+            c.device = int(device)
+        hs = (_P * n)()
+        _check(lib.crn_create_many(C.byref(c), n, hs), "crn_create_many")
+        return [cls(c, _handle=_P(hs[i])) for i in range(n)]
+
+    @staticmethod
+    def submit_many(sensors, nframes=1):
+        """Commit nframes frames on every sensor; the members of one pool, in step, are sensed by ONE launch."""
+        hs = (_P * len(sensors))(*[s._h for s in sensors])
+        _check(lib.crn_submit_many(hs, len(sensors), nframes), "crn_submit_many")
+
+    def ring_slot(self):
+        """Address of the pinned slot the next frame goes to (crn_ring_acquire)."""
+        slot = _P()
+        _check(lib.crn_ring_acquire(self._h, C.byref(slot)), "crn_ring_acquire")
+        return slot.value
 
     def close(self):
         if getattr(self, "_h", None):

@@ -50,6 +50,11 @@ struct RingSlot {
   unsigned char *d_iq = nullptr;  // device mirror
   ResultBuf res;
   SplitBuf split;
+  // where the decision of this slot is read from: the slot's own result buffer (index 0), or - for the members of a
+  // crn_create_many pool - the pool slot's buffer at the member's index
+  const ResultBuf *rv = nullptr;
+  int64_t ri = 0;
+  cudaEvent_t pool_done = nullptr;  // set while the slot's decision was launched by crn_submit_many (pool event)
   // device addresses of the pinned host buffers (zero-copy input / results), looked up once at create
   const float2 *z_iq = nullptr;
   float *z_feat = nullptr;
@@ -61,10 +66,15 @@ struct RingSlot {
   int state = 0;  // 0 free/filling, 1 in flight
 };
 
+struct Pool;
+
 }  // namespace
 
 struct crn_handle {
   crn_config cfg;
+  // crn_create_many: the handle is a member of a pool (shared pinned ring, tables, stream; see Pool below)
+  Pool *pool = nullptr;
+  int pool_index = -1;
   int device = 0;
   int num_sms = 0;
   int stride = 0;
@@ -77,6 +87,8 @@ struct crn_handle {
   float2 *d_win = nullptr;
   // group splitting (crn_sense_kernel.cuh): per-part segment sums and arrival counters, grown on demand
   int max_split = 16;       // CRN_SPLIT=<n> (read once at create) caps it; 1 disables splitting
+  int force_split = 0;      // CRN_FORCE_SPLIT=<n>: development override (tuning of pick_split's cost model)
+  double epilogue_frames = 2.0;  // pick_split: cost of one item's epilogue in units of one frame per team
   // Streaming path: from 2 MiB per decision the kernel reads the pinned slot over PCIe itself (transfer and FFTs
   // overlap frame by frame: 137 -> 127 us at 4 MiB); below that a host->device copy ahead of the kernel is quicker
   // (40 vs 43 us at 512 KiB, 27 vs 30 us at 40 KiB).  CRN_RING_COPY=1 / 0 forces the copy / the direct read (A/B).
@@ -108,6 +120,31 @@ struct crn_handle {
 };
 
 namespace {
+
+// crn_create_many: n streaming handles of one configuration on one GPU that share everything a handle owns - tables,
+// stream, and ONE pinned ring whose slot k holds the K frames of all n radios back to back ([radio][K][L], the layout
+// of a batch of n decision groups).  A member handle is a view: its ring slots point into the pool's slots, its
+// decisions are read from the pool's result arrays at its index.  crn_submit_many then senses the K-th-frame
+// decisions of all members with one copy and ONE launch of the fused kernel over n groups.
+struct Pool {
+  crn_handle *proto = nullptr;  // an ordinary handle: kernel choice, tables, launch geometry, stream
+  int n = 0;
+  int live = 0;                 // members not yet destroyed
+  size_t slot_bytes = 0;        // bytes of one member's K frames
+  struct PSlot {
+    unsigned char *h_iq = nullptr, *d_iq = nullptr;
+    const float2 *z_iq = nullptr;
+    ResultBuf res;              // n decisions, device arrays unused: the kernel writes the pinned mirrors
+    float *z_feat = nullptr;
+    double *z_ann = nullptr;
+    int32_t *z_dec = nullptr;
+    unsigned long long *z_mask = nullptr;
+    SplitBuf split;             // n * max_split * nsegs: the pooled launch, or one member's own launch at its offset
+    cudaEvent_t done = nullptr;
+  };
+  std::vector<PSlot> slots;
+  std::vector<crn_handle *> members;
+};
 
 int alloc_results(ResultBuf &r, int64_t ngroups, int nbands) {
   r.cap = ngroups;
@@ -244,6 +281,7 @@ int grid_for(const crn_handle *h, int64_t nwork) {
 // frames.  Many groups -> 1 (nothing to gain); one decision on the streaming path -> as many items as K allows.
 int pick_split(const crn_handle *h, int64_t ngroups) {
   if (h->base.upg != 0 || ngroups > h->split_max_groups) return 1;
+  if (h->force_split > 0) return (h->cfg.navg % (h->force_split * h->geo.teams) == 0) ? h->force_split : 1;
   const int K = h->cfg.navg, teams = h->geo.teams;
   const int64_t ctas = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
   int best = 1;
@@ -251,7 +289,7 @@ int pick_split(const crn_handle *h, int64_t ngroups) {
   for (int sp = 1; sp <= h->max_split; sp *= 2) {
     if (K % (sp * teams)) break;
     const int64_t rounds = (ngroups * sp + ctas - 1) / ctas;
-    const double cost = (double)rounds * ((double)(K / (sp * teams)) + 2.0);
+    const double cost = (double)rounds * ((double)(K / (sp * teams)) + h->epilogue_frames);
     if (cost < best_cost * (1.0 - 1e-9)) {
       best_cost = cost;
       best = sp;
@@ -470,6 +508,10 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
                             : h->sample_bytes * (size_t)cfg->navg * cfg->frame_len >= ((size_t)2 << 20);
     const char *cap = getenv("CRN_SPLIT");  // development override: largest split (1 = never split a group)
     if (cap && atoi(cap) >= 1) h->max_split = atoi(cap);
+    const char *fsp = getenv("CRN_FORCE_SPLIT");
+    if (fsp && atoi(fsp) >= 1) h->force_split = atoi(fsp);
+    const char *epi = getenv("CRN_EPILOGUE_FRAMES");
+    if (epi && atof(epi) >= 0.0) h->epilogue_frames = atof(epi);
     const char *force = getenv("CRN_EPI");  // "cta" | "unit": development override
     bool cta = long_even_groups;
     if (force && !strcmp(force, "cta")) cta = true;
@@ -508,14 +550,133 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     CRN_CUDA(cudaHostGetDevicePointer((void **)&s.z_dec, s.res.h_dec, 0));
     CRN_CUDA(cudaHostGetDevicePointer((void **)&s.z_mask, s.res.h_mask, 0));
     CRN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    s.rv = &s.res;
+    s.ri = 0;
   }
   guard.h = nullptr;
   *out = h;
   return CRN_OK;
 }
 
+namespace {
+void destroy_pool(Pool *p) {
+  if (!p) return;
+  if (p->proto) {
+    cudaSetDevice(p->proto->device);
+    if (p->proto->stream) cudaStreamSynchronize(p->proto->stream);
+  }
+  for (auto &ps : p->slots) {
+    cudaFreeHost(ps.h_iq);
+    cudaFree(ps.d_iq);
+    free_results(ps.res);
+    free_split_buffers(ps.split);
+    if (ps.done) cudaEventDestroy(ps.done);
+  }
+  if (p->proto) crn_destroy(p->proto);
+  delete p;
+}
+}  // namespace
+
+int crn_create_many(const crn_config *cfg, int32_t n, crn_handle **out) {
+  if (!out || n < 1) return crn::fail(CRN_ERR_INVALID, "crn_create_many: bad argument");
+  for (int i = 0; i < n; i++) out[i] = nullptr;
+  Pool *p = new (std::nothrow) Pool();
+  if (!p) return crn::fail(CRN_ERR_NOMEM, "out of host memory");
+  struct Guard {
+    Pool *p;
+    ~Guard() {
+      if (!p) return;
+      for (crn_handle *m : p->members) delete m;
+      destroy_pool(p);
+    }
+  } guard{p};
+  int st = crn_create(cfg, &p->proto);
+  if (st != CRN_OK) return st;
+  crn_handle *pr = p->proto;
+  p->n = n;
+  p->slot_bytes = pr->sample_bytes * (size_t)pr->cfg.navg * pr->cfg.frame_len;
+  const int nbands = pr->cfg.nbands;
+  const size_t per_member_scratch = (size_t)pr->max_split * pr->cfg.nsegs;
+  p->slots.resize(pr->ring.size());
+  for (auto &ps : p->slots) {
+    CRN_CUDA(cudaMallocHost(&ps.h_iq, p->slot_bytes * n));
+    CRN_CUDA(cudaMalloc(&ps.d_iq, p->slot_bytes * n));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&ps.z_iq, ps.h_iq, 0));
+    ps.res.cap = n;
+    CRN_CUDA(cudaMallocHost(&ps.res.h_feat, sizeof(float) * n * nbands));
+    CRN_CUDA(cudaMallocHost(&ps.res.h_ann, sizeof(double) * n * 3));
+    CRN_CUDA(cudaMallocHost(&ps.res.h_dec, sizeof(int32_t) * n));
+    CRN_CUDA(cudaMallocHost(&ps.res.h_mask, sizeof(unsigned long long) * n));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&ps.z_feat, ps.res.h_feat, 0));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&ps.z_ann, ps.res.h_ann, 0));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&ps.z_dec, ps.res.h_dec, 0));
+    CRN_CUDA(cudaHostGetDevicePointer((void **)&ps.z_mask, ps.res.h_mask, 0));
+    CRN_CUDA(cudaMalloc(&ps.split.d_scratch, sizeof(float) * per_member_scratch * n));
+    ps.split.scratch_cap = per_member_scratch * n;
+    CRN_CUDA(cudaMalloc(&ps.split.d_gcount, sizeof(int) * n));
+    CRN_CUDA(cudaMemset(ps.split.d_gcount, 0, sizeof(int) * n));
+    ps.split.gcount_cap = (size_t)n;
+    CRN_CUDA(cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+  }
+  for (int i = 0; i < n; i++) {
+    crn_handle *m = new (std::nothrow) crn_handle();
+    if (!m) return crn::fail(CRN_ERR_NOMEM, "out of host memory");
+    p->members.push_back(m);
+    m->cfg = pr->cfg;
+    m->pool = p;
+    m->pool_index = i;
+    m->device = pr->device;
+    m->num_sms = pr->num_sms;
+    m->stride = pr->stride;
+    m->sample_bytes = pr->sample_bytes;
+    m->allow_tma = pr->allow_tma;
+    m->launch = pr->launch;
+    m->geo = pr->geo;
+    m->base = pr->base;          // table pointers are the prototype's
+    m->max_split = pr->max_split;
+    m->force_split = pr->force_split;
+    m->epilogue_frames = pr->epilogue_frames;
+    m->ring_zero_copy = pr->ring_zero_copy;
+    m->split_max_groups = pr->split_max_groups;  // (members have no batch scratch: batch calls on a member are refused)
+    m->stream = pr->stream;       // one stream for the pool: member launches and pooled launches are ordered
+    m->ring.resize(p->slots.size());
+    for (size_t k = 0; k < m->ring.size(); k++) {
+      RingSlot &s = m->ring[k];
+      Pool::PSlot &ps = p->slots[k];
+      s.h_iq = ps.h_iq + p->slot_bytes * i;
+      s.d_iq = ps.d_iq + p->slot_bytes * i;
+      s.z_iq = reinterpret_cast<const float2 *>(reinterpret_cast<const unsigned char *>(ps.z_iq) + p->slot_bytes * i);
+      s.z_feat = ps.z_feat + (size_t)i * nbands;
+      s.z_ann = ps.z_ann + (size_t)i * 3;
+      s.z_dec = ps.z_dec + i;
+      s.z_mask = ps.z_mask + i;
+      s.split.d_scratch = ps.split.d_scratch + per_member_scratch * i;
+      s.split.scratch_cap = per_member_scratch;
+      s.split.d_gcount = ps.split.d_gcount + i;
+      s.split.gcount_cap = 1;
+      s.rv = &ps.res;
+      s.ri = i;
+      CRN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+  }
+  p->live = n;
+  for (int i = 0; i < n; i++) out[i] = p->members[i];
+  guard.p = nullptr;
+  return CRN_OK;
+}
+
 int crn_destroy(crn_handle *h) {
   if (!h) return CRN_OK;
+  if (h->pool) {  // a member owns nothing but its events; the last member to go takes the pool with it
+    Pool *p = h->pool;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &s : h->ring)
+      if (s.done) cudaEventDestroy(s.done);
+    delete h;
+    if (--p->live == 0) destroy_pool(p);
+    return CRN_OK;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
@@ -599,18 +760,97 @@ int crn_submit(crn_handle *h, int32_t nframes) {
   return CRN_OK;
 }
 
+int crn_submit_many(crn_handle *const *hs, int32_t n, int32_t nframes) {
+  if (!hs || n < 1 || nframes < 1) return crn::fail(CRN_ERR_INVALID, "crn_submit_many: bad argument");
+  for (int i = 0; i < n; i++)
+    if (!hs[i]) return crn::fail(CRN_ERR_INVALID, "crn_submit_many: null handle");
+  // One launch needs the members of one pool, all of them, all at the same point of the same slot; anything else is
+  // served handle by handle (same results, n launches).
+  Pool *p = hs[0]->pool;
+  bool poolable = p && n == p->n;
+  if (poolable) {
+    std::vector<char> seen((size_t)n, 0);
+    for (int i = 0; i < n && poolable; i++) {
+      crn_handle *h = hs[i];
+      poolable = h->pool == p && !seen[h->pool_index] && h->fill_slot == hs[0]->fill_slot &&
+                 h->fill_frames == hs[0]->fill_frames;
+      if (poolable) seen[h->pool_index] = 1;
+    }
+  }
+  if (!poolable) {
+    for (int i = 0; i < n; i++) {
+      int st = crn_submit(hs[i], nframes);
+      if (st != CRN_OK) return st;
+    }
+    return CRN_OK;
+  }
+  crn_handle *pr = p->proto;
+  const int K = pr->cfg.navg, slot = hs[0]->fill_slot, fill = hs[0]->fill_frames;
+  if (fill + nframes > K)
+    return crn::fail(CRN_ERR_INVALID, "crn_submit_many: %d frames would cross a decision boundary", nframes);
+  for (int i = 0; i < n; i++)
+    if (hs[i]->ring[slot].state != 0) return crn::fail(CRN_ERR_OVERRUN, "ring full: %d decisions unread", hs[i]->inflight);
+  if (fill + nframes < K) {
+    for (int i = 0; i < n; i++) {
+      if (fill == 0) hs[i]->ring[slot].first_frame = hs[i]->frames_seen;
+      hs[i]->fill_frames += nframes;
+      hs[i]->frames_seen += (uint64_t)nframes;
+    }
+    return CRN_OK;
+  }
+  // K-th frame of every member: one copy, one launch over n decision groups ([radio][K][L] is a batch of n groups)
+  CRN_CUDA(cudaSetDevice(pr->device));
+  Pool::PSlot &ps = p->slots[slot];
+  crn::SenseParams prm = pr->base;
+  prm.stride = pr->cfg.frame_len;  // ring slots are packed
+  if (pr->ring_zero_copy) {
+    prm.iq = ps.z_iq;
+  } else {
+    CRN_CUDA(cudaMemcpyAsync(ps.d_iq, ps.h_iq, p->slot_bytes * n, cudaMemcpyHostToDevice, pr->stream));
+    prm.iq = reinterpret_cast<const float2 *>(ps.d_iq);
+  }
+  prm.feat = ps.z_feat;
+  prm.ann = ps.z_ann;
+  prm.decision = ps.z_dec;
+  prm.mask = ps.z_mask;
+  prm.ngroups = n;
+  prm.use_tma = !pr->ring_zero_copy && (prm.upg == 0) && pr->allow_tma && ((reinterpret_cast<uintptr_t>(prm.iq) & 15) == 0) &&
+                ((pr->cfg.frame_len * pr->sample_bytes) % 16 == 0);
+  int grid = 1;
+  int st = shape_launch(pr, prm, n, ps.split, &grid);  // few radios: their K frames are dealt to several CTAs each
+  if (st != CRN_OK) return st;
+  st = pr->launch(prm, pr->cfg.window, pr->cfg.detector, grid, pr->stream, nullptr);
+  if (st != CRN_OK) return st;
+  pr->launches++;
+  CRN_CUDA(cudaEventRecord(ps.done, pr->stream));
+  for (int i = 0; i < n; i++) {
+    crn_handle *h = hs[i];
+    RingSlot &s = h->ring[slot];
+    if (fill == 0) s.first_frame = h->frames_seen;
+    h->frames_seen += (uint64_t)nframes;
+    s.pool_done = ps.done;
+    s.state = 1;
+    h->inflight++;
+    h->fill_slot = (h->fill_slot + 1) % (int)h->ring.size();
+    h->fill_frames = 0;
+  }
+  return CRN_OK;
+}
+
 static int take_result(crn_handle *h, crn_result *out, bool block) {
   if (!h || !out) return crn::fail(CRN_ERR_INVALID, "crn_poll/wait: null argument");
   if (h->inflight == 0) return crn::fail(CRN_ERR_NOT_READY, "no decision in flight");
   RingSlot &s = h->ring[h->tail_slot];
+  cudaEvent_t done = s.pool_done ? s.pool_done : s.done;
   if (block) {
-    CRN_CUDA(cudaEventSynchronize(s.done));
+    CRN_CUDA(cudaEventSynchronize(done));
   } else {
-    cudaError_t e = cudaEventQuery(s.done);
+    cudaError_t e = cudaEventQuery(done);
     if (e == cudaErrorNotReady) return CRN_ERR_NOT_READY;
     if (e != cudaSuccess) return crn::fail(CRN_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
   }
-  unpack_result(s.res, 0, h->cfg.nbands, s.first_frame, out);
+  unpack_result(*s.rv, s.ri, h->cfg.nbands, s.first_frame, out);
+  s.pool_done = nullptr;
   s.state = 0;
   h->inflight--;
   h->tail_slot = (h->tail_slot + 1) % (int)h->ring.size();
@@ -631,6 +871,7 @@ int crn_sense_batch_device(crn_handle *h, const void *d_iq, int64_t ngroups, flo
                            double *d_ann, int32_t *d_decision, uint64_t *d_mask, void *cuda_stream) {
   if (!h || !d_iq || !d_feat || ngroups < 0)
     return crn::fail(CRN_ERR_INVALID, "crn_sense_batch_device: bad argument");
+  if (h->pool) return crn::fail(CRN_ERR_UNSUPPORTED, "batch calls need a handle from crn_create, not a crn_create_many member");
   CRN_CUDA(cudaSetDevice(h->device));
   return launch(h, h->dev_split, d_iq, ngroups, d_feat, d_ann, d_decision,
                 (unsigned long long *)d_mask, (cudaStream_t)cuda_stream);
@@ -640,6 +881,7 @@ int crn_sense_batch_host(crn_handle *h, const void *iq_, int64_t ngroups, crn_re
   const unsigned char *iq = static_cast<const unsigned char *>(iq_);
   if (!h || !iq || !results || ngroups < 0)
     return crn::fail(CRN_ERR_INVALID, "crn_sense_batch_host: bad argument");
+  if (h->pool) return crn::fail(CRN_ERR_UNSUPPORTED, "batch calls need a handle from crn_create, not a crn_create_many member");
   if (ngroups == 0) return CRN_OK;
   CRN_CUDA(cudaSetDevice(h->device));
   const size_t group_bytes = h->sample_bytes * (size_t)h->stride * h->cfg.navg;
@@ -715,7 +957,11 @@ int crn_sense_batch_host(crn_handle *h, const void *iq_, int64_t ngroups, crn_re
   return drain((int)((nchunks + 1) & 1));
 }
 
-int64_t crn_launch_count(const crn_handle *h) { return h ? h->launches : 0; }
+// a pool member reports its own launches plus the pool's shared ones (crn_submit_many)
+int64_t crn_launch_count(const crn_handle *h) {
+  if (!h) return 0;
+  return h->launches + (h->pool ? h->pool->proto->launches : 0);
+}
 
 int crn_get_kernel_info(const crn_handle *h, crn_kernel_info *info) {
   if (!h || !info) return crn::fail(CRN_ERR_INVALID, "crn_get_kernel_info: null argument");

@@ -172,7 +172,11 @@ struct HybridPlan {
   // +4 % at N = 2048, +15 % at 4096, but -3 % at 8192, where the staged copy (one more shared-memory write and
   // read of the whole frame) meets a shared-memory pipe that is already ~70 % busy - there plain coalesced loads
   // behind the L2 prefetch win (435 -> 450 GS/s with 64 sub-channels, 467 -> 482 with the reference bands).
+#ifdef CRN_TMA_8192  // A/B switch
+  static constexpr bool TMA = true;
+#else
   static constexpr bool TMA = (C < 8);
+#endif
   // The window table (8 / 16 / 32 KB) lives in shared memory.  With one frame per CTA the two large ones were what
   // kept another CTA off the SM and were read through the read-only L1 path instead; with two frames per CTA
   // (4096: 2 CTAs/SM, 8192: 1) they fit, and shared memory is the faster home: 4096 +2 % (reference bands) /

@@ -159,6 +159,19 @@ int crn_ring_acquire(crn_handle *h, void **slot);
    Returns CRN_ERR_OVERRUN if every ring slot still holds an unread decision. */
 int crn_submit(crn_handle *h, int32_t nframes);
 
+/* ---- many co-located radios: one launch per decision round ------------------------------------------------------
+   The reference runs one engine per process, one process per radio (src/crts_cognitive_radio.cpp:754-812); a host
+   that senses for R radios (a CORNET rack, BASELINE configs[3]) would otherwise pay R launches per decision round.
+   crn_create_many makes R streaming handles of ONE configuration on one GPU that share their tables, their stream
+   and one pinned ring (slot layout [radio][K][L]); each is used exactly like a crn_create handle
+   (crn_ring_acquire / crn_submit / crn_poll / crn_wait / crn_reset / crn_destroy; the batch calls are refused).
+   crn_submit_many commits `nframes` frames on each of the n handles; when that completes their decisions and the
+   handles are ALL the members of one pool, in step (same slot, same frame count), the n decisions are sensed by one
+   host->device copy and ONE launch of the fused kernel over n decision groups.  Handles that do not qualify are
+   submitted one by one - same results, n launches.  Results are fetched per handle with crn_poll / crn_wait. */
+int crn_create_many(const crn_config *cfg, int32_t n, crn_handle **out /* [n] */);
+int crn_submit_many(crn_handle *const *handles, int32_t n, int32_t nframes);
+
 /* Non-blocking / blocking fetch of the oldest finished decision. */
 int crn_poll(crn_handle *h, crn_result *out);
 int crn_wait(crn_handle *h, crn_result *out);

@@ -771,3 +771,60 @@ def test_streaming_large_slots_read_in_place(crn, oracle, torch, monkeypatch, fo
     dec = np.zeros(nd, np.int32)
     check(crn, cfg, (feat, ann, dec, mask), want)
     assert [r.first_frame for r in out] == [cfg.navg * i for i in range(nd)]
+
+
+@pytest.mark.parametrize("mode,nradios", [("ref", 37), ("welch", 64)])
+def test_many_radios_share_one_launch(crn, oracle, torch, mode, nradios):
+    """crn_create_many / crn_submit_many: R co-located radios, one pinned ring, ONE launch per decision round.  Every
+    radio's decisions equal the oracle on that radio's frames (and a plain streaming handle fed the same frames, to
+    fp32 rounding: the launch shapes differ); rounds go past the ring depth; a subset of the handles, or handles out
+    of step, fall back to per-handle launches with the same results."""
+    cfg = crn.config_reference() if mode == "ref" else crn.config_welch(1024, 8)
+    K, L = cfg.navg, cfg.frame_len
+    rounds = 6
+    rng = np.random.default_rng(7)
+    sc = crn.synth_config(cfg.group_samples, dwell_groups=2, snr_db=10.0, seed=5)
+    iq = [oracle.synth(sc, rounds * K * L, stream=r)[0].reshape(rounds, K, L) for r in range(nradios)]
+    sensors = crn.Sensor.create_many(cfg, nradios, device=0)
+    plain = crn.Sensor(cfg, device=0)
+    try:
+        base = sensors[0].launches
+        got = [[] for _ in range(nradios)]
+        for rd in range(rounds):
+            for k in range(K):
+                for r, s in enumerate(sensors):
+                    C.memmove(s.ring_slot(), iq[r][rd, k].ctypes.data, L * 8)
+                crn.Sensor.submit_many(sensors, 1)
+            for r, s in enumerate(sensors):
+                res = s.wait()
+                assert res.first_frame == rd * K
+                got[r].append((np.array(res.feat[:cfg.nbands]), np.array(res.ann_out[:]), res.decision))
+        assert sensors[0].launches - base == rounds          # one launch per round, whatever R is
+        for r in range(nradios):
+            of, oa, od, _ = oracle.sense_port(cfg, iq[r].ravel())
+            gf = np.stack([g[0] for g in got[r]])
+            assert feat_err(gf, of) <= FEAT_RTOL
+            assert np.abs(np.stack([g[1] for g in got[r]]) - oa).max() <= ANN_ATOL
+            assert [g[2] for g in got[r]] == od.tolist()
+        # the same frames through an ordinary streaming handle
+        for rd in range(2):
+            for k in range(K):
+                plain.push_frame(iq[3][rd, k])
+            res = plain.wait()
+            assert np.allclose(np.array(res.feat[:cfg.nbands]), got[3][rd][0], rtol=2e-6, atol=0) and res.decision == got[3][rd][2]
+        # a subset is not "the whole pool": served handle by handle, still right
+        sub = sensors[: nradios // 2]
+        for k in range(K):
+            for r, s in enumerate(sub):
+                C.memmove(s.ring_slot(), iq[r][0, k].ctypes.data, L * 8)
+            crn.Sensor.submit_many(sub, 1)
+        for r, s in enumerate(sub):
+            res = s.wait()
+            assert np.allclose(np.array(res.feat[:cfg.nbands]), got[r][0][0], rtol=2e-6, atol=0) and res.decision == got[r][0][2]
+        # batch calls on a member are refused, loudly
+        with pytest.raises(crn.CrnError):
+            sensors[0].sense_host(iq[0].ravel())
+    finally:
+        for s in sensors:
+            s.close()
+        plain.close()
