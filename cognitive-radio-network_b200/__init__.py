@@ -30,6 +30,7 @@ DECIDE_NONE, DECIDE_ANN, DECIDE_ENERGY = 0, 1, 2
 ALL_BUSY, CH1_OCCUPIED, CH2_OCCUPIED, CH3_OCCUPIED = 0, 1, 2, 3
 IQ_CF32, IQ_SC16 = 0, 1
 INTF_NONE, INTF_CW, INTF_NOISE, INTF_AWGN = 0, 1, 2, 3  # src/interferer.cpp waveforms that need no modem
+INTF_GMSK, INTF_RRC, INTF_OFDM = 4, 5, 6              # ... and the framed ones (:156-288)
 
 # TX retune the reference performs for each decision (CE_Predictive_Node.cpp:245-261, .hpp:55-57)
 TX_FREQ_FOR_DECISION = {ALL_BUSY: None, CH1_OCCUPIED: 835e6, CH2_OCCUPIED: 833e6, CH3_OCCUPIED: 835e6}
@@ -78,7 +79,7 @@ class SynthConfig(C.Structure):
         ("seed", C.c_uint64), ("fs", C.c_double), ("pu_rate", C.c_double), ("offsets_hz", C.c_double * 3),
         ("snr_db", C.c_double), ("pu_gain_db", C.c_double), ("hop_mode", C.c_int32),
         ("dwell_groups", C.c_int32), ("group_samples", C.c_int32),
-        ("intf_type", C.c_int32), ("intf_period_groups", C.c_int32), ("reserved_", C.c_int32),
+        ("intf_type", C.c_int32), ("intf_period_groups", C.c_int32), ("pu_framed", C.c_int32),
         ("intf_offset_hz", C.c_double), ("intf_rate", C.c_double), ("intf_gain_db", C.c_double),
         ("intf_duty", C.c_double),
     ]

@@ -273,7 +273,9 @@ typedef struct crn_synth_config {
   int32_t intf_type;    /* enum crn_interferer: 0 none */
   int32_t intf_period_groups; /* duty-cycle period in decision groups (its wall-clock `period`, interferer.cpp:28,
                            395-409, scaled like the PU dwell); <= 0: always on */
-  int32_t reserved_;
+  int32_t pu_framed;    /* 0: the PU sends payload OFDM symbols back to back; 1: flex-frame structure of transmit_frame
+                           (src/extensible_cognitive_radio.cpp:883-949): frames of 32 symbols = S0, S0, S1, 7 header
+                           symbols (BPSK), 22 payload symbols (QPSK) */
   double intf_offset_hz;/* interferer tx_freq - fc */
   double intf_rate;     /* its sample rate (tx_rate); every generated sample is held for fs/intf_rate receiver samples */
   double intf_gain_db;  /* soft gain (default -3 dB, interferer.cpp:32) plus whatever path loss is wanted */
@@ -283,7 +285,22 @@ typedef struct crn_synth_config {
 /* Interference waveforms of src/interferer.cpp that need no modem: CW = the constant 0.5+0.5j of
    BuildCWTransmission (:128-134), NOISE = uniform in [-0.25, 0.25) per component (BuildNOISETransmission
    :136-142), AWGN = Gaussian with MEAN 5 and sigma 5 per component, as coded (dist(5.0, 5.0) :24, :144-154). */
-enum crn_interferer { CRN_INTF_NONE = 0, CRN_INTF_CW = 1, CRN_INTF_NOISE = 2, CRN_INTF_AWGN = 3 };
+/* ... and the three that need one (BuildGMSKTransmission :156-221, BuildRRCTransmission :223-253,
+   BuildOFDMTransmission :255-288).  liquid-dsp's frame generators are absent, so frames are restated at the level the
+   sensing path can see - pulse shape, symbol rate, frame cadence, constant-envelope / PAPR character - with random
+   symbols in place of liquid's coded header/payload bits:
+     GMSK  BT = 0.5, modulation index 1/2, 2 samples/symbol interpolated by 2 (:189-205) = 4 samples/symbol; frames
+           of 1024 symbols followed by the 12 padding samples of :212-219;
+     RRC   QPSK symbols +-0.25 +- 0.25j (:237-240) zero-stuffed to 2 samples/symbol through the 129-tap root raised
+           cosine (beta 0.35, semi-length 32, :61-65), filter reset every 200-sample frame (:231); as coded the
+           "stop a filter length before the end" test (:236) never fires (unsigned arithmetic), so all 100 symbols
+           of a frame are sent;
+     OFDM  64 subcarriers, cyclic prefix 16, taper 6 (:23-24,66-71), liquid's default allocation; frames of 22
+           symbols = S0, S0, S1, 7 header symbols (BPSK), 12 payload symbols (QPSK: 128 bytes + CRC32 over 44 data
+           subcarriers), back to back.
+   Like the other waveforms they are generated at the interferer's rate and held to the receiver's. */
+enum crn_interferer { CRN_INTF_NONE = 0, CRN_INTF_CW = 1, CRN_INTF_NOISE = 2, CRN_INTF_AWGN = 3,
+                      CRN_INTF_GMSK = 4, CRN_INTF_RRC = 5, CRN_INTF_OFDM = 6 };
 
 int crn_synth_config_default(crn_synth_config *sc, int32_t group_samples);
 

@@ -277,6 +277,125 @@ static void subcarrier(uint64_t sseed, int64_t m, int k, float *re, float *im) {
   }
 }
 
+/* ---- framed waveforms (include/crnsense.h: pu_framed, CRN_INTF_GMSK / RRC / OFDM) ------------------------------- */
+#define PU_FRAME_SYMS 32 /* S0 S0 S1, 7 header, 22 payload symbols (ecr.cpp:883-949 through ofdmflexframegen) */
+#define OF_FRAME_SYMS 22 /* S0 S0 S1, 7 header, 12 payload symbols (interferer.cpp:255-288) */
+#define OF_TAPER 6       /* interferer.hpp:24 */
+#define RRC_HLEN 129     /* 2 * RRC_SAMPS_PER_SYM * RRC_FILTER_SEMILENGTH + 1 (interferer.cpp:61) */
+#define RRC_FRAME 200    /* RRC_SYMS_PER_FRAME * RRC_SAMPS_PER_SYM (interferer.hpp:18-19) */
+#define GM_SYMS 1024
+#define GM_SPS 4         /* k = 2 (liquid gmskframegen) x the half-band interpolator (interferer.cpp:60,201-204) */
+#define GM_FRAME (GM_SYMS * GM_SPS + 12) /* + zero padding (interferer.cpp:212-219) */
+
+/* subcarrier k of the symbol at position fm of a flex frame; uid keys the random header/payload symbols */
+static void frame_cell(uint64_t sseed, int64_t uid, int fm, int k, float *re, float *im) {
+  *re = *im = 0.0f;
+  if (uid < 0) return;
+  if (fm <= 1) { /* S0: fixed sequence on the even subcarriers */
+    if (k % 2 == 0) *re = (mix64(0x5330ull * 0x9E3779B97F4A7C15ull + (uint64_t)(k + 64)) & 1) ? 0.20412414523193151f : -0.20412414523193151f;
+  } else if (fm == 2) { /* S1: fixed sequence on every used subcarrier */
+    *re = (mix64(0x5331ull * 0x9E3779B97F4A7C15ull + (uint64_t)(k + 64)) & 1) ? 0.14142135623730950f : -0.14142135623730950f;
+  } else if (fm < 10) { /* header: BPSK */
+    *re = (mix64(sseed ^ mix64((uint64_t)uid * 128u + (uint64_t)(k + 64))) & 1) ? 0.14142135623730950f : -0.14142135623730950f;
+  } else {
+    subcarrier(sseed, uid, k, re, im);
+  }
+}
+
+/* sum over the used subcarriers at phase z (z^k by recurrence), current symbol and - inside the taper - the previous one */
+static void symbol_sum(uint64_t sseed, int64_t m, int frame_syms, float zr, float zi, int in_taper, float ramp,
+                       float *vr, float *vi) {
+  float ar = 0.0f, ai = 0.0f, br = 0.0f, bi = 0.0f, pr = zr, pi = zi;
+  const int fm = frame_syms ? (int)(m % frame_syms) : 0, fp = frame_syms ? (int)((m - 1 + frame_syms) % frame_syms) : 0;
+  for (int k = 1; k <= SY_HALF; k++) {
+    float xr, xi, yr, yi;
+    if (frame_syms) { frame_cell(sseed, m, fm, k, &xr, &xi); frame_cell(sseed, m, fm, -k, &yr, &yi); }
+    else { subcarrier(sseed, m, k, &xr, &xi); subcarrier(sseed, m, -k, &yr, &yi); }
+    ar += xr * pr - xi * pi + yr * pr + yi * pi;
+    ai += xr * pi + xi * pr - yr * pi + yi * pr;
+    if (in_taper) {
+      if (frame_syms) { frame_cell(sseed, m - 1, fp, k, &xr, &xi); frame_cell(sseed, m - 1, fp, -k, &yr, &yi); }
+      else { subcarrier(sseed, m - 1, k, &xr, &xi); subcarrier(sseed, m - 1, -k, &yr, &yi); }
+      br += xr * pr - xi * pi + yr * pr + yi * pi;
+      bi += xr * pi + xi * pr - yr * pi + yi * pr;
+    }
+    const float nr = pr * zr - pi * zi;
+    pi = pr * zi + pi * zr;
+    pr = nr;
+  }
+  *vr = ramp * ar + (1.0f - ramp) * br;
+  *vi = ramp * ai + (1.0f - ramp) * bi;
+}
+
+/* liquid_firdes_rrcos(k = 2, m = 32, beta = 0.35, dt = 0, h) as recalled (liquid absent): tap i sits at z = i/2 - 32 symbols */
+static float rrc_tap(int i) {
+  const double beta = 0.35, z = (double)i / 2.0 - 32.0, g = 1.0 - 16.0 * beta * beta * z * z;
+  if (fabs(z) < 1e-5) return (float)(1.0 - beta + 4.0 * beta / M_PI);
+  if (fabs(g) < 1e-5)
+    return (float)(beta / sqrt(2.0) * ((1.0 + 2.0 / M_PI) * sin(M_PI / (4.0 * beta)) + (1.0 - 2.0 / M_PI) * cos(M_PI / (4.0 * beta))));
+  return (float)((4.0 * beta / (M_PI * g)) * (cos((1.0 + beta) * M_PI * z) + sin((1.0 - beta) * M_PI * z) / (4.0 * beta * z)));
+}
+/* GMSK phase pulse for BT = 0.5: a bit turns the phase by (pi/2) q(t - n - 1/2), q(x) = I(x + 1/2) - I(x - 1/2),
+   I(u) = integral of the normal CDF Phi(c v) up to u = u Phi(c u) + phi(c u) / c,  c = 2 pi BT / sqrt(ln 2) */
+static double gmsk_q(double x) {
+  const double c = 2.0 * M_PI * 0.5 / sqrt(log(2.0));
+  const double a = x + 0.5, b = x - 0.5;
+  const double Ia = a * 0.5 * erfc(-c * a / sqrt(2.0)) + exp(-0.5 * c * c * a * a) / (sqrt(2.0 * M_PI) * c);
+  const double Ib = b * 0.5 * erfc(-c * b / sqrt(2.0)) + exp(-0.5 * c * c * b * b) / (sqrt(2.0 * M_PI) * c);
+  return Ia - Ib;
+}
+static uint32_t gmsk_word(uint64_t sseed, uint64_t F, int w) {
+  return (uint32_t)mix64(sseed ^ mix64(0x474D534B00000000ull + F * 64ull + (uint64_t)w));
+}
+
+/* sample `im` of the interferer's own stream for the waveforms that need a modem */
+static void modem_sample(int type, uint64_t sseed, uint64_t im, float *re, float *imag) {
+  *re = *imag = 0.0f;
+  if (type == CRN_INTF_RRC) {
+    static float h[RRC_HLEN];
+    static int have;
+    if (!have) { for (int i = 0; i < RRC_HLEN; i++) h[i] = rrc_tap(i <= RRC_HLEN / 2 ? i : RRC_HLEN - 1 - i); have = 1; }
+    const uint64_t F = im / RRC_FRAME;
+    const int j = (int)(im % RRC_FRAME);
+    /* firfilt reset at the frame start (:231), then y[j] = sum_i h[i] x[j-i] with a symbol on every even sample */
+    for (int n = 0; 2 * n <= j; n++) {
+      const int tap = j - 2 * n;
+      if (tap >= RRC_HLEN) continue;
+      const uint64_t hs = mix64(sseed ^ mix64(0x5252430000000000ull + F * 128ull + (uint64_t)n));
+      *re = fmaf((hs & 1) ? 0.25f : -0.25f, h[tap], *re);
+      *imag = fmaf((hs & 2) ? 0.25f : -0.25f, h[tap], *imag);
+    }
+  } else if (type == CRN_INTF_GMSK) {
+    const uint64_t F = im / GM_FRAME;
+    const int j = (int)(im % GM_FRAME);
+    if (j >= GM_SYMS * GM_SPS) return;
+    const int n0 = j / GM_SPS, sub = j % GM_SPS;
+    int turns = 0; /* bits whose pulse has fully passed: +-1 quarter turn each */
+    for (int n = 0; n <= n0 - 3; n++) turns += ((gmsk_word(sseed, F, n >> 5) >> (n & 31)) & 1u) ? 1 : -1;
+    float frac = 0.0f;
+    for (int d = -2; d <= 2; d++) {
+      const int n = n0 + d;
+      if (n < 0 || n >= GM_SYMS) continue;
+      const float b = ((gmsk_word(sseed, F, n >> 5) >> (n & 31)) & 1u) ? 1.0f : -1.0f;
+      frac = fmaf(b, (float)gmsk_q(-(double)d + (double)sub / 4.0 - 0.5), frac);
+    }
+    const float quarter = (float)(((turns % 4) + 4) % 4) + frac;
+    *re = cosf(1.5707963267948966f * quarter);
+    *imag = sinf(1.5707963267948966f * quarter);
+  } else if (type == CRN_INTF_OFDM) {
+    const int64_t m = (int64_t)(im / SY_SYM);
+    const int tau = (int)(im % SY_SYM);
+    const float th = (float)(tau - SY_CP) * (1.0f / SY_M);
+    const float zr = cosf(6.283185307179586f * th), zi = sinf(6.283185307179586f * th);
+    float ramp = 1.0f;
+    if (tau < OF_TAPER) {
+      const float sn = sinf(1.5707963267948966f * ((float)tau + 0.5f) * (1.0f / OF_TAPER));
+      ramp = sn * sn;
+    }
+    symbol_sum(sseed ^ 0x4F46444D4F46444Dull, m, OF_FRAME_SYMS, zr, zi, tau < OF_TAPER, ramp, re, imag);
+  }
+}
+
 double crn_oracle_synth_sigma2(const crn_synth_config *sc) {
   const double ps = pow(10.0, sc->pu_gain_db / 10.0);
   const double bocc = (2.0 * SY_HALF + 1.0) / SY_M * sc->pu_rate;
@@ -305,27 +424,10 @@ static void synth_range(const crn_synth_config *sc, uint64_t stream_seed, const 
       const float sn = sinf(1.5707963267948966f * tau * (1.0f / SY_TAPER));
       ramp = sn * sn;
     }
-    float ar = 0.0f, ai = 0.0f; /* current symbol */
-    float br = 0.0f, bi = 0.0f; /* previous symbol's cyclic postfix (same phases: tau+64 == tau mod 64) */
-    float pr = zr, pi = zi;     /* z^k */
-    for (int k = 1; k <= SY_HALF; k++) {
-      float xr, xi, yr, yi;
-      subcarrier(stream_seed, m, k, &xr, &xi);
-      subcarrier(stream_seed, m, -k, &yr, &yi);
-      ar += xr * pr - xi * pi + yr * pr + yi * pi;
-      ai += xr * pi + xi * pr - yr * pi + yi * pr;
-      if (in_taper) {
-        subcarrier(stream_seed, m - 1, k, &xr, &xi);
-        subcarrier(stream_seed, m - 1, -k, &yr, &yi);
-        br += xr * pr - xi * pi + yr * pr + yi * pi;
-        bi += xr * pi + xi * pr - yr * pi + yi * pr;
-      }
-      const float nr = pr * zr - pi * zi;
-      pi = pr * zi + pi * zr;
-      pr = nr;
-    }
-    float vr = gain * (ramp * ar + (1.0f - ramp) * br);
-    float vi = gain * (ramp * ai + (1.0f - ramp) * bi);
+    float sumr, sumi; /* current symbol, blended with the previous symbol's cyclic postfix inside the taper */
+    symbol_sum(stream_seed, m, sc->pu_framed ? PU_FRAME_SYMS : 0, zr, zi, in_taper, ramp, &sumr, &sumi);
+    float vr = gain * sumr;
+    float vi = gain * sumi;
     /* mix to the channel offset */
     const double cyc = (double)s * (sc->offsets_hz[ch] / sc->fs);
     const float ph = (float)(cyc - floor(cyc));
@@ -346,7 +448,9 @@ static void synth_range(const crn_synth_config *sc, uint64_t stream_seed, const 
       if (period <= 0 || (s % period) < on) {
         const uint64_t im = (uint64_t)((double)s * (sc->intf_rate / sc->fs));
         float br2 = 0.5f, bi2 = 0.5f;
-        if (sc->intf_type != CRN_INTF_CW) {
+        if (sc->intf_type >= CRN_INTF_GMSK) {
+          modem_sample(sc->intf_type, stream_seed, im, &br2, &bi2);
+        } else if (sc->intf_type != CRN_INTF_CW) {
           const uint64_t hi = mix64(stream_seed ^ mix64(0x1F7E2A5C00000000ull + 2ull * im));
           const float v1 = (float)(hi >> 40) * (1.0f / 16777216.0f), v2 = (float)((hi >> 16) & 0xFFFFFF) * (1.0f / 16777216.0f);
           if (sc->intf_type == CRN_INTF_NOISE) {

@@ -50,7 +50,7 @@ class SynthConfig(C.Structure):
         ("seed", C.c_uint64), ("fs", C.c_double), ("pu_rate", C.c_double), ("offsets_hz", C.c_double * 3),
         ("snr_db", C.c_double), ("pu_gain_db", C.c_double), ("hop_mode", C.c_int32),
         ("dwell_groups", C.c_int32), ("group_samples", C.c_int32),
-        ("intf_type", C.c_int32), ("intf_period_groups", C.c_int32), ("reserved_", C.c_int32),
+        ("intf_type", C.c_int32), ("intf_period_groups", C.c_int32), ("pu_framed", C.c_int32),
         ("intf_offset_hz", C.c_double), ("intf_rate", C.c_double), ("intf_gain_db", C.c_double),
         ("intf_duty", C.c_double),
     ]

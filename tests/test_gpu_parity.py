@@ -343,6 +343,70 @@ def test_synth_kernel_matches_cpu_statement(crn, oracle, torch):
     assert np.array_equal(d_part.cpu().numpy().view(np.complex64).ravel(), got[2 * gs: 2 * gs + 1000])
 
 
+def _spectrum_facts(iq):
+    """(mean power, PAPR in dB, 99 % occupied bandwidth as a fraction of the sample rate) of a complex capture."""
+    p = np.abs(iq) ** 2
+    X = np.fft.fftshift(np.abs(np.fft.fft(iq[: iq.size // 4096 * 4096].reshape(-1, 4096), axis=1)) ** 2).mean(axis=0)
+    c = np.cumsum(X) / X.sum()
+    return p.mean(), 10 * np.log10(p.max() / p.mean()), (np.searchsorted(c, 0.995) - np.searchsorted(c, 0.005)) / 4096.0
+
+
+def test_interferer_modems_and_framed_pu(crn, oracle, torch):
+    """the interferer waveforms that need a modem (src/interferer.cpp:156-288: GMSK, root-raised-cosine
+    QPSK, OFDM bursts) and the flex-frame structure of the PU (src/extensible_cognitive_radio.cpp:883-949).
+    GPU == CPU statement to 2e-4, and the waveforms have the spectra their modems imply."""
+    gs = 65536
+    n = 4 * gs
+    stream = torch.cuda.current_stream().cuda_stream
+    d_iq = torch.empty(n, 2, dtype=torch.float32, device="cuda")
+
+    def both(sc):
+        crn.synth_generate(sc, d_iq, 0, n, None, 0, stream)
+        torch.cuda.synchronize()
+        return d_iq.cpu().numpy().view(np.complex64).ravel().copy(), oracle.synth(sc, n)[0]
+
+    # (1) on top of the PU, at the interferer's own rate (held to the receiver's), offset and duty-cycled
+    for itype, rate in ((crn.INTF_GMSK, 1e6), (crn.INTF_RRC, 1e6), (crn.INTF_OFDM, 2e6)):
+        got, want = both(crn.synth_config(gs, dwell_groups=2, snr_db=10.0, seed=12, intf_type=itype, intf_rate=rate,
+                                          intf_offset_hz=-4.5e6, intf_period_groups=2, intf_duty=0.75, intf_gain_db=-3.0))
+        assert np.abs(got - want).max() <= 2e-4, itype
+    # (2) alone (PU and noise switched off) at one interferer sample per receiver sample: the modem's own spectrum
+    facts = {}
+    for itype in (crn.INTF_GMSK, crn.INTF_RRC, crn.INTF_OFDM):
+        got, want = both(crn.synth_config(gs, pu_gain_db=-300.0, snr_db=200.0, intf_type=itype, intf_rate=13e6,
+                                          intf_gain_db=0.0, intf_offset_hz=0.0))
+        assert np.abs(got - want).max() <= 2e-4, itype
+        facts[itype] = _spectrum_facts(got)
+    pw, papr, bw = facts[crn.INTF_GMSK]      # constant envelope, 4 samples/symbol, BT = 0.5: 99 % bandwidth ~1.04 Rs
+    assert abs(pw - 1.0) < 0.01 and papr < 0.05 and 0.24 < bw < 0.28
+    pw, papr, bw = facts[crn.INTF_RRC]       # 2 samples/symbol, beta 0.35: inside (1 + beta) Rs = 0.675 fs
+    assert 0.07 < pw < 0.10 and 3.0 < papr < 7.0 and 0.5 < bw < 0.675
+    pw, papr, bw = facts[crn.INTF_OFDM]      # 51 of 64 subcarriers, unit power, Gaussian-like envelope
+    assert abs(pw - 1.0) < 0.05 and 8.0 < papr < 13.0 and 0.76 < bw < 0.83
+    # (3) framed PU: same power and occupied bandwidth as the payload-only stream, S0's half-empty comb shows up
+    got_f, want_f = both(crn.synth_config(gs, snr_db=200.0, pu_framed=1))
+    got_u, _ = both(crn.synth_config(gs, snr_db=200.0, pu_framed=0))
+    assert np.abs(got_f - want_f).max() <= 2e-4
+    pf, _, bf = _spectrum_facts(got_f)
+    pu, _, bu = _spectrum_facts(got_u)
+    assert abs(pf / pu - 1.0) < 0.05 and abs(bf - bu) < 0.01
+    assert np.abs(got_f - got_u).max() > 0.05      # a different waveform (preamble / header symbols) ...
+    # ... that the sensing path treats alike: same decisions on both captures
+    cfg = crn.config_welch(1024, 64)
+    feats = []
+    for framed in (0, 1):
+        sc = crn.synth_config(gs, dwell_groups=1, snr_db=10.0, seed=3, pu_framed=framed)
+        crn.synth_generate(sc, d_iq, 0, n, None, 0, stream)
+        d_feat = torch.empty(4, 4, dtype=torch.float32, device="cuda")
+        d_dec = torch.empty(4, dtype=torch.int32, device="cuda")
+        with crn.Sensor(cfg, device=0) as sn:
+            sn.sense_device(d_iq, 4, d_feat, None, d_dec, None, stream)
+        torch.cuda.synchronize()
+        feats.append((d_feat.cpu().numpy(), d_dec.cpu().numpy()))
+    assert np.array_equal(feats[0][1], feats[1][1])
+    assert np.allclose(feats[0][0], feats[1][0], rtol=0.25)
+
+
 def test_multi_radio_streams(crn, oracle, torch):
     """BASELINE configs[3] shape: independent sensing streams (simulated CORNET nodes), 2048-pt FFT, one
     decision group per stream, every stream with its own seed / hop chain / noise."""

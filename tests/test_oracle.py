@@ -263,3 +263,25 @@ def test_reference_arm_never_loads_the_product_library():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0
     assert line["native_so_mapped"] and all(m.startswith("oracle/") for m in line["native_so_mapped"]), line["native_so_mapped"]
+
+
+def test_modem_waveforms_have_their_spectra(oracle):
+    """CPU statement of the interferer modems (src/interferer.cpp:156-288), observed alone at their own rate: GMSK is
+    constant-envelope with ~1.04 Rs of 99 % bandwidth (BT = 0.5, 4 samples/symbol), root-raised-cosine QPSK stays
+    inside (1 + beta) Rs, the OFDM burst fills 51/64 of the band with a Gaussian-like envelope."""
+    gs = 65536
+
+    def facts(itype):
+        sc = oracle.synth_config(gs, pu_gain_db=-300.0, snr_db=200.0, intf_type=itype, intf_rate=13e6, intf_gain_db=0.0)
+        iq, _ = oracle.synth(sc, 4 * gs)
+        p = np.abs(iq) ** 2
+        X = np.fft.fftshift(np.abs(np.fft.fft(iq.reshape(-1, 4096), axis=1)) ** 2).mean(axis=0)
+        c = np.cumsum(X) / X.sum()
+        return p.mean(), 10 * np.log10(p.max() / p.mean()), (np.searchsorted(c, 0.995) - np.searchsorted(c, 0.005)) / 4096.0
+
+    pw, papr, bw = facts(4)
+    assert abs(pw - 1.0) < 0.01 and papr < 0.05 and 0.24 < bw < 0.28
+    pw, papr, bw = facts(5)
+    assert 0.07 < pw < 0.10 and 3.0 < papr < 7.0 and 0.5 < bw < 0.675
+    pw, papr, bw = facts(6)
+    assert abs(pw - 1.0) < 0.05 and 8.0 < papr < 13.0 and 0.76 < bw < 0.83
