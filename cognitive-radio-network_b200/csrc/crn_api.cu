@@ -470,6 +470,8 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
   }
   b.nbands = cfg->nbands;
   b.nsegs = cfg->nsegs;
+  b.seg_stride = (cfg->nsegs + 7) & ~7;    // shared-memory scratch rows of the epilogue are sized to the band plan
+  b.band_stride = (cfg->nbands + 7) & ~7;
   b.postop = cfg->postop;
   b.decide = cfg->decide;
   b.threshold = cfg->ann_threshold;

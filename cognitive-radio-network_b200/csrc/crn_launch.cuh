@@ -2,6 +2,7 @@
 // Each crn_sense_n<N>.cu includes this once, so the six sizes compile in parallel.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "crn_internal.h"
@@ -25,7 +26,10 @@ typedef int (*sense_launch_fn)(const SenseParams &prm, int window, int detector,
 template <class P, bool WIN, int DET, int EPI, bool SC16, unsigned AMASK>
 int launch_msk(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeometry *geo) {
   auto kern = sense_kernel<P, WIN, DET, EPI, SC16, AMASK>;
-  const size_t smem = P::smem_bytes(WIN);
+  // CRN_EXTRA_SMEM=<bytes>: development switch - unused dynamic shared memory on top, to move the SM's L1 / shared
+  // carve-out without touching the kernel (the streaming loads are sensitive to the L1 size)
+  static const size_t extra = getenv("CRN_EXTRA_SMEM") ? (size_t)atol(getenv("CRN_EXTRA_SMEM")) : 0;
+  const size_t smem = P::smem_bytes(WIN, EPI == EPI_CTA, prm.seg_stride, prm.band_stride) + extra;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
   if (geo) {

@@ -66,6 +66,7 @@ struct SenseParams {
   float *scratch;        // [ngroups][split][nsegs] per-part segment sums (split > 1)
   int *gcount;           // [ngroups] parts arrived, zero between launches (split > 1)
   int sc16;              // IQ buffers hold int16 pairs (4 B/sample) instead of float pairs
+  int seg_stride, band_stride;  // row lengths of the epilogue's shared-memory scratch: nsegs / nbands rounded up to 8
   unsigned acc_mask;     // bit m set: some band segment reads a bin held in accumulator register m
   double threshold, energy_factor;
   double wih[CRN_ANN_INPUTS + 1][CRN_ANN_HIDDEN + 1];
@@ -89,7 +90,14 @@ struct Plan {
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
   static constexpr bool HYBRID = false;
   static constexpr int C = 1;
-  static constexpr bool WIN_SMEM = true;           // window table staged in shared memory
+  // The window pairs (N/2 float2) are read through the L1 instead of shared memory at N >= 512: the streaming loads
+  // are sensitive to how much of the SM's 256 KB is left as L1 (4 CTAs x 44 KB -> 196 KB carve-out; x 40 KB -> 164 KB:
+  // +1.3 % at N = 1024, profiles/r02f_l1probe.txt; forcing the 228 KB carve-out costs 13-19 %).  -DCRN_PLAN_WIN_SMEM: A/B
+#ifdef CRN_PLAN_WIN_SMEM
+  static constexpr bool WIN_SMEM = true;
+#else
+  static constexpr bool WIN_SMEM = (N < 512);
+#endif
   // spectrum bin held in accumulator register m of team thread t after the last pass
   __host__ __device__ static constexpr int bin_of(int t, int m) { return t + T * m; }
   // Bulk-copy (TMA) staging of the next frame pays off where a frame spans several warps and every
@@ -114,9 +122,11 @@ struct Plan {
   static_assert(R0 >= 16, "first radix < 16 would bank-conflict the exchange");
   static_assert(T >= 16 && (T <= 32 ? 32 % T == 0 : T % 32 == 0), "team must tile a warp");
   static_assert(NT % UNIT_THREADS == 0 && (T <= 32 || UNITS <= 15), "units must tile the CTA (named barriers 1..15)");
-  static constexpr size_t smem_bytes(bool win) {
-    return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win ? N / 2 : 0)) +
-           sizeof(float) * (2 * UNITS * CRN_MAX_SEGS + CRN_MAX_BANDS * UNITS) + sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
+  // epi_cta: the CTA-wide epilogue needs one row of segment sums and one feature row, not the per-unit two-slot ring
+  static constexpr size_t smem_bytes(bool win, bool epi_cta, int seg_stride = CRN_MAX_SEGS, int band_stride = CRN_MAX_BANDS) {
+    return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win && WIN_SMEM ? N / 2 : 0)) +
+           sizeof(float) * (epi_cta ? seg_stride + band_stride : 2 * UNITS * seg_stride + band_stride * UNITS) +
+           sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
   }
 };
 
@@ -190,9 +200,10 @@ struct HybridPlan {
   static_assert(C == 2 || C == 4 || C == 8, "hybrid plans cover N = 2048, 4096, 8192");
   static_assert(UNITS <= 15, "named barriers 1..15");
   __host__ __device__ static constexpr int bin_of(int t, int m) { return C * ((t & 31) + 32 * m) + (t >> 5); }
-  static constexpr size_t smem_bytes(bool win) {
+  static constexpr size_t smem_bytes(bool win, bool epi_cta, int seg_stride = CRN_MAX_SEGS, int band_stride = CRN_MAX_BANDS) {
     return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win && WIN_SMEM ? N / 2 : 0)) +
-           sizeof(float) * (2 * UNITS * CRN_MAX_SEGS + CRN_MAX_BANDS * UNITS) + sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
+           sizeof(float) * (epi_cta ? seg_stride + band_stride : 2 * UNITS * seg_stride + band_stride * UNITS) +
+           sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
   }
 };
 
@@ -453,8 +464,30 @@ __host__ __device__ constexpr unsigned full_acc_mask() { return E >= 32 ? 0xFFFF
 //              warp busy when groups are short (reference mode: K = 10) or K does not divide by TEAMS.
 enum { EPI_CTA = 0, EPI_UNIT = 1 };
 
+// Resident CTAs per SM an instantiation is compiled for (__launch_bounds__).  Plan::MINB is what every instantiation
+// of a size fits; some fit more without spilling (tools/ptxas_report.py): the kernels pruned to the reference band plan
+// lack ~22 accumulators (96 instead of 122-128 registers at N = 512 / 1024: one CTA more), the 16-point-per-thread plan of
+// N = 256 runs in 80.  Taken only when that many CTAs also fit the SM's shared memory (228 KB, 1 KB reserved per CTA).
+template <int N>
+struct MoreCtas { static constexpr int cta_all = 0, cta_pruned = 0, unit_pruned = 0; };  // 0: Plan::MINB
+#ifndef CRN_NO_MORE_CTAS  // A/B switch
+template <> struct MoreCtas<256> { static constexpr int cta_all = 6, cta_pruned = 6, unit_pruned = 0; };
+#ifdef CRN_MORE_CTAS_512_1024  // measured: 5 CTAs x 96 registers lose 12-18 % at N = 512 / 1024 (5 x 44 KB of shared
+                               // memory push the carve-out to 228 KB and leave the streaming loads a 28 KB L1)
+template <> struct MoreCtas<512> { static constexpr int cta_all = 0, cta_pruned = 5, unit_pruned = 5; };
+template <> struct MoreCtas<1024> { static constexpr int cta_all = 0, cta_pruned = 5, unit_pruned = 0; };
+#endif
+#endif
+template <class P, bool WIN, int EPI, unsigned AMASK>
+__host__ __device__ constexpr int min_ctas() {
+  constexpr bool pruned = AMASK != full_acc_mask<P::E>();
+  constexpr int want = (EPI == EPI_CTA) ? (pruned ? MoreCtas<P::N>::cta_pruned : MoreCtas<P::N>::cta_all)
+                                        : (pruned ? MoreCtas<P::N>::unit_pruned : 0);
+  return (want > P::MINB && (P::smem_bytes(WIN, EPI == EPI_CTA) + 1024) * (size_t)want <= (size_t)228 * 1024) ? want : P::MINB;
+}
+
 template <class P, bool WIN, int DET, int EPI, bool SC16, unsigned AMASK>
-__global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams prm) {
+__global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_kernel(const SenseParams prm) {
   using sample_t = typename std::conditional<SC16, unsigned, float2>::type;  // one IQ sample in memory
   constexpr int SPL = 128 / (int)sizeof(sample_t);                           // samples per 128-byte line
   const sample_t *const iq = reinterpret_cast<const sample_t *>(prm.iq);
@@ -468,9 +501,11 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
   float2 *winp_s = xbuf + (size_t)TEAMS * P::XSZ;
   constexpr bool WSM = WIN && P::WIN_SMEM;
   const float2 *winp = WSM ? winp_s : prm.winp;  // window pairs: shared copy, or read-only global path
-  float *segpart = reinterpret_cast<float *>(winp_s + (WSM ? N / 2 : 0));  // [2][UNITS][CRN_MAX_SEGS]
-  float *featbuf = segpart + 2 * UNITS * CRN_MAX_SEGS;                    // [UNITS][CRN_MAX_BANDS]
-  int *cnt = reinterpret_cast<int *>(featbuf + UNITS * CRN_MAX_BANDS);    // [2][UNITS] arrivals
+  // unit epilogue: [2][UNITS][seg_stride] partial sums + [UNITS][band_stride] features; CTA epilogue: one row each
+  float *segpart = reinterpret_cast<float *>(winp_s + (WSM ? N / 2 : 0));
+  const int SEGS = prm.seg_stride, BANDS = prm.band_stride;  // row lengths (the launch sized the allocation with them)
+  float *featbuf = segpart + (EPI == EPI_CTA ? SEGS : 2 * UNITS * SEGS);
+  int *cnt = reinterpret_cast<int *>(featbuf + (EPI == EPI_CTA ? BANDS : UNITS * BANDS));  // [2][UNITS] arrivals
   volatile int *done = cnt + 2 * UNITS;                                   // [2][UNITS] completed combines
   unsigned long long *mbars = reinterpret_cast<unsigned long long *>(
       (reinterpret_cast<uintptr_t>(cnt + 4 * UNITS) + 7) & ~(uintptr_t)7);  // [TEAMS] TMA arrival barriers
@@ -666,7 +701,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
     const int ipart = (int)(w - g * S);        // which K/S-frame slice of it
     if constexpr (EPI == EPI_CTA) {
       // ---- per-group epilogue, CTA-wide ----------------------------------------------------------------
-      float *segsum = segpart;  // [CRN_MAX_SEGS]
+      float *segsum = segpart;  // [seg_stride]
       __syncthreads();          // every team finished reading its exchange buffer
       {
         float *mypart = reinterpret_cast<float *>(xb);  // N floats per team, aliasing the exchange buffer
@@ -773,7 +808,7 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
         }
       }
       __syncwarp();
-      float *mine = segpart + ((size_t)slot * UNITS + unit) * CRN_MAX_SEGS;
+      float *mine = segpart + ((size_t)slot * UNITS + unit) * SEGS;
       for (int sb = wu; sb < prm.nsegs; sb += 4 * NWU) {  // four segments per trip (independent chains)
         float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
@@ -807,13 +842,13 @@ __global__ void __launch_bounds__(P::NT, P::MINB) sense_kernel(const SenseParams
       last = __shfl_sync(0xffffffffu, last, 0);
       if (last) {
         __threadfence_block();
-        float *fb = featbuf + unit * CRN_MAX_BANDS;
-        const float *sp = segpart + ((size_t)slot * UNITS + (size_t)gl * upg) * CRN_MAX_SEGS;
+        float *fb = featbuf + unit * BANDS;
+        const float *sp = segpart + ((size_t)slot * UNITS + (size_t)gl * upg) * SEGS;
         for (int b = lane; b < prm.nbands; b += 32) {
           float m = 0.0f;
           for (int s = 0; s < prm.nsegs; s++)
             if (prm.seg_band[s] == b)
-              for (int u = 0; u < upg; u++) m += sp[u * CRN_MAX_SEGS + s];
+              for (int u = 0; u < upg; u++) m += sp[u * SEGS + s];
           m *= prm.invK;
           const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
           fb[b] = f;
