@@ -268,8 +268,22 @@ int pick_upg(int units, int teams_per_unit, int K) {
   return best;
 }
 
+// Grid of a launch.  Round 1 launched exactly as many CTAs as fit the GPU at once and let each stride over its share
+// of the work items.  Equal shares are not equal times: the SMs of a B200 do not see HBM at the same speed (ncu: the
+// per-SM active cycles of one launch spread by 6 %, and a resident warp slot is empty 17 % of the time), so the
+// kernel ran at the pace of its slowest SM.  Large launches are therefore cut into `waves` times more CTAs than fit
+// at once - the hardware block scheduler hands the next CTA to whichever SM frees a slot first, which is dynamic load
+// balancing for the price of re-staging a few KB of tables per CTA.  Measured (profiles/r02i_gridmult.txt, same box):
+// N = 1024 789 -> 836 GS/s (0.965 -> 1.02 of the measured copy peak), with every bin live 675 -> 742; 512 794 -> 834;
+// reference mode 736 -> 782; 2048 638 -> 674; 4096 547 -> 578 at 8 waves; N = 8192 (one CTA per SM, compute/latency
+// bound) gains nothing and stays persistent.  CRN_GRID_MULT=<waves> overrides (development).
+int grid_waves(const crn_handle *h) {
+  static const int forced = getenv("CRN_GRID_MULT") ? atoi(getenv("CRN_GRID_MULT")) : 0;
+  if (forced >= 1) return forced;
+  return h->cfg.nfft <= 2048 ? 16 : (h->cfg.nfft == 4096 ? 8 : 1);
+}
 int grid_for(const crn_handle *h, int64_t nwork) {
-  int64_t g = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1);
+  int64_t g = (int64_t)h->num_sms * (h->geo.ctas_per_sm > 0 ? h->geo.ctas_per_sm : 1) * grid_waves(h);
   const int64_t gl = h->base.upg > 0 ? h->geo.units / h->base.upg : 1;  // groups a CTA works on at a time
   const int64_t need = (nwork + gl - 1) / gl;
   if (need < g) g = need;

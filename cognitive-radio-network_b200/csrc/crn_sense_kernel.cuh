@@ -170,6 +170,12 @@ struct HybridPlan {
 #else
   static constexpr bool OWN_SHARE = (C == 2);
 #endif
+  // C = 4 / 8: a warp keeps the 1/C of pass A's outputs that is its own through a warp-uniform switch on the warp index
+  // (one straight-line copy of the exchange per warp, static register indices in each).  -DCRN_KEEP_OWN=<max C>: A/B
+#ifndef CRN_KEEP_OWN
+#define CRN_KEEP_OWN 4
+#endif
+  static constexpr bool KEEP_OWN = (C > 2 && C <= CRN_KEEP_OWN);
   static constexpr int TW1 = FOLD_C ? 8 * T : 8 * 32;  // pass-C twisted-codelet table: 8 rows, one column per team thread / lane
   static constexpr int TW2 = 8 * C + (FOLD_C ? 0 : T);  // pass-B table: 8 rows, one column per warp (+ {u, u w^16} per thread)
   static constexpr int UNIT_THREADS = T;
@@ -635,6 +641,50 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
             a[2 * i] = a[i];
           });
           static_for<0, E / 2>([&](auto I) { a[2 * I.value + 1] = wb[lane + 32 * I.value]; });
+        } else if constexpr (P::KEEP_OWN) {
+          // C = 4: warp w keeps z_w[n] for its own threads' n (8 of 32 values per thread) and sends the other three
+          // sub-sequences: 24 stores + 24 loads per thread instead of 32 + 32.  As at C = 2, warp r transforms its
+          // sub-sequence circularly shifted by 32 r samples (|Y| unchanged, bins in place), which makes the register
+          // roles of pass B the same in every warp: kept values are inputs q = 4 i, the values from the warp d ahead
+          // (mod 4) inputs 4 i + d.  The senders know everything statically inside a warp-uniform switch on their warp
+          // index: the slot, and - for the one value per destination that wraps around the shifted sequence - the factor
+          // W_N^(-1024 r) = j^r (a swap and a sign).  The kept values are picked out of the radix-4 outputs by selects.
+          static_assert(C == 4, "keep-own exchange: the wrap factor is a quarter turn only at C = 4");
+          reg_pass_first<E, C, T, WIN>(a, winp, t);  // a[i + r G] = z_r[t + T i]
+          const int w = t >> 5;
+          team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
+          static_for<0, C>([&](auto W) {
+            if (w == W.value) {
+              static_for<0, C>([&](auto R) {
+                if constexpr (R.value != W.value) {
+                  constexpr int d = (W.value - R.value + C) % C;
+                  float2 *dst = xb + R.value * P::RS + (d - 1) * G * 32 + lane;
+                  if constexpr (W.value > R.value) {
+                    static_for<0, G>([&](auto I) { dst[I.value * 32] = a[I.value + R.value * G]; });
+                  } else {
+                    const float2 v = a[R.value * G];  // n < 32 r: wraps to the end of warp r's shifted sequence
+                    dst[(G - 1) * 32] = R.value == 1 ? make_float2(-v.y, v.x)
+                                                     : (R.value == 2 ? make_float2(-v.x, -v.y) : make_float2(v.y, -v.x));
+                    static_for<1, G>([&](auto I) { dst[(I.value - 1) * 32] = a[I.value + R.value * G]; });
+                  }
+                }
+              });
+            }
+          });
+          team_sync<T>(team);
+          float2 own[G];
+          static_for<0, G>([&](auto I) {
+            float2 o = a[I.value];
+            static_for<1, C>([&](auto R) {
+              o.x = (w == R.value) ? a[I.value + R.value * G].x : o.x;
+              o.y = (w == R.value) ? a[I.value + R.value * G].y : o.y;
+            });
+            own[I.value] = o;
+          });
+          static_for<0, G>([&](auto I) {
+            a[C * I.value] = own[I.value];
+            static_for<1, C>([&](auto D) { a[C * I.value + D.value] = wb[((D.value - 1) * G + I.value) * 32 + lane]; });
+          });
         } else {
         reg_pass_first<E, C, T, WIN>(a, winp, t);
         // the one team-wide exchange: y_r[n] (n = t + T*i) goes to warp r's region, linear in n
