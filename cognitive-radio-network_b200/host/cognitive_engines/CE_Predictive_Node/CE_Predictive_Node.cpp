@@ -149,7 +149,8 @@ void CE_Predictive_Node::execute() {
     config = 1;
 #ifdef CRN_ECR_HAS_RX_SLOT_PROVIDER
     // from now on the receiver may recv() straight into the pinned ring (no memcpy here or under CE_mutex)
-    ECR->set_rx_slot_provider(&CE_Predictive_Node::rx_slot, this);
+    if (!getenv("CRN_ENGINE_COPY"))  // CRN_ENGINE_COPY=1: keep upstream's two copies per packet (A/B of the handoff)
+      ECR->set_rx_slot_provider(&CE_Predictive_Node::rx_slot, this);
 #endif
     if (!quiet && (cfg.nfft != 512 || cfg.detector != CRN_DET_MAG || cfg.postop != CRN_POST_SQUARE_OF_SUM ||
                    cfg.window != CRN_WINDOW_RECT) && !custom_weights)
