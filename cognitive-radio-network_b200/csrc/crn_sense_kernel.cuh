@@ -90,13 +90,20 @@ struct Plan {
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
   static constexpr bool HYBRID = false;
   static constexpr int C = 1;
+  // Window pairs from the table (false) or computed from two per-thread seeds (true; see HybridPlan::WIN_CALC).
+  // -DCRN_WIN_CALC_SMALL=<smallest N that computes>: A/B switch for the one-warp-per-frame plans.
+#ifdef CRN_WIN_CALC_SMALL
+  static constexpr bool WIN_CALC = (N >= CRN_WIN_CALC_SMALL);
+#else
+  static constexpr bool WIN_CALC = false;
+#endif
   // The window pairs (N/2 float2) are read through the L1 instead of shared memory at N >= 512: the streaming loads
   // are sensitive to how much of the SM's 256 KB is left as L1 (4 CTAs x 44 KB -> 196 KB carve-out; x 40 KB -> 164 KB:
   // +1.3 % at N = 1024, profiles/r02f_l1probe.txt; forcing the 228 KB carve-out costs 13-19 %).  -DCRN_PLAN_WIN_SMEM: A/B
 #ifdef CRN_PLAN_WIN_SMEM
-  static constexpr bool WIN_SMEM = true;
+  static constexpr bool WIN_SMEM = !WIN_CALC;
 #else
-  static constexpr bool WIN_SMEM = (N < 512);
+  static constexpr bool WIN_SMEM = (N < 512) && !WIN_CALC;
 #endif
   // spectrum bin held in accumulator register m of team thread t after the last pass
   __host__ __device__ static constexpr int bin_of(int t, int m) { return t + T * m; }
@@ -157,6 +164,18 @@ struct HybridPlan {
   // the 196 KB shared-memory carve-out and leaves the SM with a 28 KB L1: measured -8 %).  !FOLD_C (N = 8192): pass B
   // multiplies its column by u = W_N^(j r) in its first stage (+32 packed instructions per frame and thread, one
   // 16-byte read of {u, u w^16}); pass C then uses the 4 KB table of the 1024-point FFT.
+  // The Hann window is computed, not read (round 3): thread t needs w[t + T m] = 1/2 - 1/2 cos(theta_t + m Delta),
+  // theta_t = 2 pi t / (N - 1), Delta = 2 pi T / (N - 1), and cos(theta_t + m Delta) = cos(theta_t) cos(m Delta) -
+  // sin(theta_t) sin(m Delta) with cos / sin(m Delta) compile-time immediates and (cos, sin)(theta_t) two per-thread
+  // registers: two scalar FFMA per window value instead of half a 64-bit shared-memory read.  The hybrid kernels are
+  // bound by the L1 / shared-memory data pipe (ncu: 70 % busy at N = 8192, 84 % at 2048, the highest pipe of the SM),
+  // the window pairs were 32 of ~430 wavefronts per 1024 samples, and the table (N/2 float2: 16 / 32 KB) is what kept
+  // the FOLD_C table out of the 196 KB carve-out at N = 8192.  -DCRN_WIN_CALC_MINC=<C>: smallest C that computes (A/B;
+  // 99 = never).  Not at C = 2: the own-share exchange bakes a per-warp sign into the pairs.
+#ifndef CRN_WIN_CALC_MINC
+#define CRN_WIN_CALC_MINC 4
+#endif
+  static constexpr bool WIN_CALC = (C >= CRN_WIN_CALC_MINC);
 #if defined(CRN_FOLD_C_ALL)   // A/B switches (build.py --variant)
   static constexpr bool FOLD_C = true;
 #elif defined(CRN_FOLD_B_ALL)
@@ -198,9 +217,9 @@ struct HybridPlan {
   // (4096: 2 CTAs/SM, 8192: 1) they fit, and shared memory is the faster home: 4096 +2 % (reference bands) /
   // +4 % (64 sub-channels), 8192 -1 % / +5 %.  -DCRN_WIN_L1 restores the L1 path from 4096 up (A/B).
 #ifdef CRN_WIN_L1
-  static constexpr bool WIN_SMEM = (N < 4096);
+  static constexpr bool WIN_SMEM = (N < 4096) && !WIN_CALC;
 #else
-  static constexpr bool WIN_SMEM = true;
+  static constexpr bool WIN_SMEM = !WIN_CALC;
 #endif
   static constexpr bool PREFETCH = true;           // hybrid plans: +2 % (2048) ... +5 % (8192) with
   static_assert(C == 2 || C == 4 || C == 8, "hybrid plans cover N = 2048, 4096, 8192");
@@ -290,9 +309,22 @@ __device__ __forceinline__ void team_sync(int team) {
   }
 }
 
+// Hann window value w[t + T M] of an N-point frame from the per-thread seeds (cos, sin)(2 pi t / (N - 1)):
+// 1/2 - 1/2 cos(theta_t + M Delta), Delta = 2 pi T / (N - 1), by the angle-addition formula with cos / sin(M Delta)
+// as immediates (liquid-dsp's symmetric Hann, CE extension; the table path evaluates the same formula in float on the
+// host, the two agree to ~1e-7 absolute).
+template <int N, int T, int M>
+__device__ __forceinline__ float hann_calc(float2 seed) {
+  constexpr float hc = (float)(-0.5 * cx_cos_turn(M * T, N - 1));
+  constexpr float hs = (float)(0.5 * cx_sin_turn(M * T, N - 1));
+  return fmaf(seed.y, hs, fmaf(seed.x, hc, 0.5f));
+}
+enum { WIN_NONE = 0, WIN_TABLE = 1, WIN_COMPUTED = 2 };
+
 // Pass 0: E/R radix-R FFTs on registers {i + q*(E/R)}; the window (if any) rides on the first stage.
-template <int E, int R, int T, bool WIN>
-__device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__restrict__ winp, int t) {
+template <int E, int R, int T, int WMODE>
+__device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__restrict__ winp, int t,
+                                               float2 wseed = make_float2(0.f, 0.f)) {
   constexpr int G = E / R;
   constexpr int LOG = ilog2(R);
   static_for<0, G>([&](auto I) {
@@ -300,9 +332,12 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
     static_for<0, R / 2>([&](auto Q) {
       constexpr int m0 = I.value + Q.value * G;  // partner is register m0 + E/2
       constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
-      if constexpr (WIN) {
+      if constexpr (WMODE == WIN_TABLE) {
         const float2 w = winp[m0 * T + t];
         butterfly_w_real(a[m0], a[m0 + E / 2], w.x, w.y, v[br], v[br + 1]);
+      } else if constexpr (WMODE == WIN_COMPUTED) {
+        butterfly_w_real(a[m0], a[m0 + E / 2], hann_calc<E * T, T, m0>(wseed), hann_calc<E * T, T, m0 + E / 2>(wseed),
+                         v[br], v[br + 1]);
       } else {
         v[br] = add2(a[m0], a[m0 + E / 2]);
         v[br + 1] = sub2(a[m0], a[m0 + E / 2]);
@@ -507,6 +542,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
   float2 *winp_s = xbuf + (size_t)TEAMS * P::XSZ;
   constexpr bool WSM = WIN && P::WIN_SMEM;
   const float2 *winp = WSM ? winp_s : prm.winp;  // window pairs: shared copy, or read-only global path
+  constexpr int WMODE = !WIN ? WIN_NONE : (P::WIN_CALC ? WIN_COMPUTED : WIN_TABLE);
   // unit epilogue: [2][UNITS][seg_stride] partial sums + [UNITS][band_stride] features; CTA epilogue: one row each
   float *segpart = reinterpret_cast<float *>(winp_s + (WSM ? N / 2 : 0));
   const int SEGS = prm.seg_stride, BANDS = prm.band_stride;  // row lengths (the launch sized the allocation with them)
@@ -519,6 +555,12 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
   const int tid = threadIdx.x;
   const int team = tid / T;
   const int t = tid % T;
+  float2 wseed = make_float2(0.f, 0.f);  // (cos, sin)(2 pi t / (N - 1)): seeds of the computed window (hann_calc)
+  if constexpr (WMODE == WIN_COMPUTED) {
+    double sn, cs;
+    sincospi(2.0 * (double)t / (double)(N - 1), &sn, &cs);
+    wseed = make_float2((float)cs, (float)sn);
+  }
   const int unit = tid / UT;            // reduction unit of this thread
   const int ut = tid % UT;              // thread index inside the unit
   const int upg = (EPI == EPI_CTA) ? UNITS : prm.upg;
@@ -569,16 +611,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
     // frame pointers advance by plain 64-bit adds inside the loop; the multiplications happen once per item
     const size_t fstep = (size_t)FT * (size_t)prm.stride;  // samples between this team's frames
     const sample_t *x = first_frame(w) + t;
-    // first frame this team senses in the CTA's next item (prefetch target at the item boundary);
-    // "+ (SPL-1) t" turns the per-thread sample pointer into a per-thread 128-byte line pointer
-    const sample_t *xng = (w + gstep < prm.nwork) ? first_frame(w + gstep) + t + (SPL - 1) * t : nullptr;
     for (int k = fs; k < KP; k += FT, x += fstep) {
-      if constexpr (PREFETCH) {
-        // the frame this team senses next: k + FT of this group, else its first frame of the next
-        // group.  One frame of compute covers the DRAM latency, so the loads below hit L2.
-        const sample_t *nx = (k + FT < KP) ? x + fstep + (SPL - 1) * t : xng;
-        if (nx) prefetch_frame_l2<E, T>(nx, (int)frame_bytes - 128 * t);
-      }
       float2 a[E];
       if (tma) {
         // the frame was pulled into this team's buffer (linear layout) by the bulk copy issued one frame ago
@@ -598,6 +631,23 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
       } else {
 #pragma unroll
         for (int m = 0; m < E; m++) a[m] = (t + T * m < L) ? ld_stream(x + T * m) : make_float2(0.f, 0.f);
+      }
+      if constexpr (PREFETCH) {
+        // Pull the frame this team senses next towards L2: k + FT of this item, else its first frame of the CTA's next
+        // item.  One frame of compute covers the DRAM latency, so the loads above hit L2.  Issued AFTER this frame's
+        // loads (round 3): the address used to be a select between two values kept alive across the whole frame loop -
+        // spilled in the all-bins kernels, and the loads queued behind those local-memory reads (3 % of the N = 8192
+        // kernel's warp time sat on that select); the item-boundary address is now rebuilt in its rare branch.
+        // "+ (SPL-1) t" turns the per-thread sample pointer into a per-thread 128-byte line pointer.
+        const sample_t *nx;
+        if (k + FT < KP) nx = x + fstep + (SPL - 1) * t;
+        else nx = (w + gstep < prm.nwork) ? first_frame(w + gstep) + t + (SPL - 1) * t : nullptr;
+        if (nx) prefetch_frame_l2<E, T>(nx, (int)frame_bytes - 128 * t);
+      }
+      if constexpr (WMODE == WIN_COMPUTED) {
+        // the 32 window values are loop-invariant; hoisted out of the frame loop they would be 32 more live registers
+        // (spilled).  The empty asm makes the seeds opaque per frame, so the values are rebuilt where they are used.
+        asm volatile("" : "+f"(wseed.x), "+f"(wseed.y));
       }
       if constexpr (P::HYBRID) {
         constexpr int C = P::C, G = E / C;
@@ -620,9 +670,12 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           const float sg = w ? -1.0f : 1.0f;
           static_for<0, E / 2>([&](auto I) {
             float2 p, q;
-            if constexpr (WIN) {
+            if constexpr (WMODE == WIN_TABLE) {
               const float2 wp = winp[I.value * T + t];  // { w[n], (+/-) w[n + N/2] }
               butterfly_w_real(a[I.value], a[I.value + E / 2], wp.x, wp.y, p, q);
+            } else if constexpr (WMODE == WIN_COMPUTED) {
+              butterfly_w_real(a[I.value], a[I.value + E / 2], hann_calc<N, T, I.value>(wseed),
+                               sg * hann_calc<N, T, I.value + E / 2>(wseed), p, q);
             } else {
               p = fma2(a[I.value + E / 2], bc2(sg), a[I.value]);
               q = fma2(a[I.value + E / 2], bc2(-sg), a[I.value]);
@@ -649,8 +702,9 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           // (mod 4) inputs 4 i + d.  The senders know everything statically inside a warp-uniform switch on their warp
           // index: the slot, and - for the one value per destination that wraps around the shifted sequence - the factor
           // W_N^(-1024 r) = j^r (a swap and a sign).  The kept values are picked out of the radix-4 outputs by selects.
-          static_assert(C == 4, "keep-own exchange: the wrap factor is a quarter turn only at C = 4");
-          reg_pass_first<E, C, T, WIN>(a, winp, t);  // a[i + r G] = z_r[t + T i]
+          // (C = 8, -DCRN_KEEP_OWN=8: the wrap factor W_N^(-1024 r) is an eighth turn - one complex multiply by a
+          // constant for the one wrapped value per destination.)
+          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed);  // a[i + r G] = z_r[t + T i]
           const int w = t >> 5;
           team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
           static_for<0, C>([&](auto W) {
@@ -663,8 +717,13 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
                     static_for<0, G>([&](auto I) { dst[I.value * 32] = a[I.value + R.value * G]; });
                   } else {
                     const float2 v = a[R.value * G];  // n < 32 r: wraps to the end of warp r's shifted sequence
-                    dst[(G - 1) * 32] = R.value == 1 ? make_float2(-v.y, v.x)
-                                                     : (R.value == 2 ? make_float2(-v.x, -v.y) : make_float2(v.y, -v.x));
+                    if constexpr (C == 4) {
+                      dst[(G - 1) * 32] = R.value == 1 ? make_float2(-v.y, v.x)
+                                                       : (R.value == 2 ? make_float2(-v.x, -v.y) : make_float2(v.y, -v.x));
+                    } else {  // v * exp(+j 2 pi r / C)
+                      constexpr float cr = (float)cx_cos_turn(R.value, C), sr = (float)cx_sin_turn(R.value, C);
+                      dst[(G - 1) * 32] = make_float2(fmaf(v.x, cr, -v.y * sr), fmaf(v.x, sr, v.y * cr));
+                    }
                     static_for<1, G>([&](auto I) { dst[(I.value - 1) * 32] = a[I.value + R.value * G]; });
                   }
                 }
@@ -686,7 +745,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
             static_for<1, C>([&](auto D) { a[C * I.value + D.value] = wb[((D.value - 1) * G + I.value) * 32 + lane]; });
           });
         } else {
-        reg_pass_first<E, C, T, WIN>(a, winp, t);
+        reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed);
         // the one team-wide exchange: y_r[n] (n = t + T*i) goes to warp r's region, linear in n
         team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
         static_for<0, G>([&](auto I) {
@@ -711,7 +770,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         else reg_pass_twisted<E, 32, 32, 32, 32>(a, tw1, lane);
       } else {
       // pass 0 (Ns = 1: no twiddles; window folded in)
-      reg_pass_first<E, P::R0, T, WIN>(a, winp, t);
+      reg_pass_first<E, P::R0, T, WMODE>(a, winp, t, wseed);
       exchange<E, P::R0, T, 1, P::PADSHIFT>(a, xb, t, team);
       // after the frame's last exchange the buffer is free: start pulling this team's next frame now, so
       // the copy flies under the remaining butterflies and the accumulate
