@@ -190,27 +190,115 @@ __device__ __forceinline__ void butterfly_rt(float2 &a, float2 &b, float c, floa
 template <int RS>
 struct TwistedTable {
   const float4 *__restrict__ col;  // this thread's column of the table; rows are RS float4 apart
-  template <int E>
-  __device__ __forceinline__ float2 entry() const {
-    const float4 w = col[(E / 2) * RS];
-    return (E & 1) ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
-  }
+  template <int ROW>
+  __device__ __forceinline__ float4 row() const { return col[ROW * RS]; }
 };
-template <int R, int FIRST, int RS>
-__device__ __forceinline__ void fft_dit_twisted(float2 (&v)[R], const TwistedTable<RS> tw) {
+
+// ---- tensor memory (TMEM) as a per-thread table store ----------------------------------------------------------
+// Blackwell's 256 KB of tensor memory per SM (512 columns x 128 lanes x 32 bit) is idle in a kernel without MMAs, and
+// tcgen05.ld / tcgen05.st move it to and from registers through their own pipe, not the L1 / shared-memory data pipe
+// that bounds the hybrid FFT plans.  With the .32x32b shape thread i of a warp owns lane 32 (warp % 4) + i and reads
+// consecutive columns: a private, loop-invariant table of the thread - exactly what the twisted codelets' twiddle
+// columns are.  A thread only ever reads what it wrote itself, so no cross-thread ordering is involved.
+__device__ __forceinline__ void tmem_st4(unsigned taddr, float4 v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v.x)),
+               "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A tcgen05.ld in flight: the registers it will fill.  tmem_wait hands them out - the wait instruction carries them as
+// in/out operands, so nothing can consume them early, while independent arithmetic is free to move in between.
+struct TmemPending4 { unsigned x, y, z, w; };
+struct TmemPending8 { unsigned r[8]; };
+__device__ __forceinline__ TmemPending4 tmem_issue4(unsigned taddr) {
+  TmemPending4 p;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w) : "r"(taddr));
+  return p;
+}
+__device__ __forceinline__ float4 tmem_wait(TmemPending4 p) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(p.x), "+r"(p.y), "+r"(p.z), "+r"(p.w));
+  return make_float4(__uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z), __uint_as_float(p.w));
+}
+__device__ __forceinline__ TmemPending8 tmem_issue8(unsigned taddr) {
+  TmemPending8 p;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(p.r[0]), "=r"(p.r[1]), "=r"(p.r[2]), "=r"(p.r[3]), "=r"(p.r[4]), "=r"(p.r[5]), "=r"(p.r[6]), "=r"(p.r[7])
+               : "r"(taddr));
+  return p;
+}
+__device__ __forceinline__ void tmem_wait(TmemPending8 p, float4 &a, float4 &b) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(p.r[0]), "+r"(p.r[1]), "+r"(p.r[2]), "+r"(p.r[3]), "+r"(p.r[4]), "+r"(p.r[5]), "+r"(p.r[6]), "+r"(p.r[7]));
+  a = make_float4(__uint_as_float(p.r[0]), __uint_as_float(p.r[1]), __uint_as_float(p.r[2]), __uint_as_float(p.r[3]));
+  b = make_float4(__uint_as_float(p.r[4]), __uint_as_float(p.r[5]), __uint_as_float(p.r[6]), __uint_as_float(p.r[7]));
+}
+__device__ __forceinline__ void tmem_wait(TmemPending8 p, float (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(p.r[0]), "+r"(p.r[1]), "+r"(p.r[2]), "+r"(p.r[3]), "+r"(p.r[4]), "+r"(p.r[5]), "+r"(p.r[6]), "+r"(p.r[7]));
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(p.r[i]);
+}
+__device__ __forceinline__ float4 tmem_ld4(unsigned taddr) { return tmem_wait(tmem_issue4(taddr)); }
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float4 &a, float4 &b) { tmem_wait(tmem_issue8(taddr), a, b); }
+struct TmemTwistedTable {
+  unsigned taddr;  // TMEM address (lane base of the warp | first column) of this thread's rows, 4 columns per row
+  template <int ROW>
+  __device__ __forceinline__ float4 row() const { return tmem_ld4(taddr + 4 * ROW); }
+};
+
+template <int R, int FIRST, class Table>
+__device__ __forceinline__ void fft_dit_twisted(float2 (&v)[R], const Table tw) {
   constexpr int LOG = ilog2(R);
   static_for<FIRST, LOG + 1>([&](auto S) {
     constexpr int m = 1 << S.value;
     constexpr int h = m >> 1;
     constexpr int cnt = (m >= 4) ? m / 4 : 1;
     constexpr int base = (m >= 4) ? m / 4 : 0;
-    static_for<0, cnt>([&](auto J) {
-      const float2 tau = tw.template entry<base + J.value>();
-      static_for<0, R / m>([&](auto B) {
-        constexpr int k = B.value * m + J.value;
-        butterfly_rt(v[k], v[k + h], tau.x, -tau.y);
-        if constexpr (m >= 4) butterfly_rt(v[k + cnt], v[k + cnt + h], tau.y, tau.x);  // -j tau
+    // entries base .. base + cnt - 1, two per table row
+    static_for<0, (cnt + 1) / 2>([&](auto JR) {
+      const float4 rw = tw.template row<(base + 2 * JR.value) / 2>();
+      static_for<0, (cnt >= 2 ? 2 : 1)>([&](auto H) {
+        constexpr int e = base + 2 * JR.value + H.value;
+        constexpr int J = e - base;
+        const float2 tau = (e & 1) ? make_float2(rw.z, rw.w) : make_float2(rw.x, rw.y);
+        static_for<0, R / m>([&](auto B) {
+          constexpr int k = B.value * m + J;
+          butterfly_rt(v[k], v[k + h], tau.x, -tau.y);
+          if constexpr (m >= 4) butterfly_rt(v[k + cnt], v[k + cnt + h], tau.y, tau.x);  // -j tau
+        });
       });
+    });
+  });
+}
+
+// The whole twisted radix-R codelet (stage 1 included) with the table rows fetched from tensor memory one row ahead:
+// row r + 1 is in flight while the butterflies of row r run (a row feeds 4 .. R/2 butterflies, the load takes ~12
+// cycles).  Entry e of the table belongs to stage m = 2 (e = 0) or m = 4 << floor(log2 e), J = e - m/4.
+template <int R>
+__device__ __forceinline__ void fft_dit_twisted_tmem(float2 (&v)[R], unsigned taddr) {
+  TmemPending4 pend = tmem_issue4(taddr);
+  static_for<0, R / 4>([&](auto ROW) {
+    const float4 rw = tmem_wait(pend);
+    if constexpr (ROW.value + 1 < R / 4) pend = tmem_issue4(taddr + 4 * (ROW.value + 1));
+    static_for<0, 2>([&](auto H) {
+      constexpr int e = 2 * ROW.value + H.value;
+      const float2 tau = H.value ? make_float2(rw.z, rw.w) : make_float2(rw.x, rw.y);
+      if constexpr (e == 0) {
+        static_for<0, R / 2>([&](auto B) { butterfly_rt(v[2 * B.value], v[2 * B.value + 1], tau.x, -tau.y); });
+      } else {
+        constexpr int m = 4 << ilog2(e), h = m / 2, cnt = m / 4, J = e - cnt;
+        static_for<0, R / m>([&](auto B) {
+          constexpr int k = B.value * m + J;
+          butterfly_rt(v[k], v[k + h], tau.x, -tau.y);
+          butterfly_rt(v[k + cnt], v[k + cnt + h], tau.y, tau.x);  // -j tau
+        });
+      }
     });
   });
 }

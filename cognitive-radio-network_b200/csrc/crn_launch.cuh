@@ -39,6 +39,25 @@ int launch_msk(const SenseParams &prm, int grid, cudaStream_t stream, LaunchGeom
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P::NT, smem);
     if (e != cudaSuccess) return fail(CRN_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    if constexpr (P::TMEM_TW) {
+      // The occupancy API answers 1 CTA/SM for a kernel that allocates tensor memory, whatever it allocates; the
+      // hardware keeps as many CTAs resident as registers, shared memory, threads and TMEM columns allow (ncu, N = 2048:
+      // block limits registers 2 / shared memory 2, 15.6 of 16 warps active).  Count them here.
+      int dev = 0, regs_sm = 0, smem_sm = 0, thr_sm = 0, smem_rsv = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+      cudaDeviceGetAttribute(&smem_rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+      const int regs_cta = ((fa.numRegs + 7) / 8) * 8 * P::NT;
+      const size_t smem_cta = smem + fa.sharedSizeBytes + (size_t)smem_rsv;
+      int n = regs_cta > 0 ? regs_sm / regs_cta : 1;
+      if (smem_cta > 0 && (int)((size_t)smem_sm / smem_cta) < n) n = (int)((size_t)smem_sm / smem_cta);
+      if (thr_sm / P::NT < n) n = thr_sm / P::NT;
+      const int tmem = 512 / (int)tmem_alloc_cols(P::TMEM_COLS_PER_WARP * (P::NT / 128));
+      if (tmem < n) n = tmem;
+      if (n > occ) occ = n;
+    }
     geo->ctas_per_sm = occ;
     geo->smem_bytes = (int)smem;
     geo->regs = fa.numRegs;

@@ -89,7 +89,9 @@ struct Plan {
   static constexpr int UNITS = NT / UNIT_THREADS;  // reduction units per CTA
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
   static constexpr bool HYBRID = false;
+  static constexpr bool TMEM_TW = false, WIN_TMEM = false, ACC_TMEM = false;
   static constexpr int C = 1;
+  static constexpr int TW_SMEM = TW1 + TW2;        // float4 rows of the twiddle tables staged in shared memory
   // Window pairs from the table (false) or computed from two per-thread seeds (true; see HybridPlan::WIN_CALC).
   // -DCRN_WIN_CALC_SMALL=<smallest N that computes>: A/B switch for the one-warp-per-frame plans.
 #ifdef CRN_WIN_CALC_SMALL
@@ -107,6 +109,8 @@ struct Plan {
 #endif
   // spectrum bin held in accumulator register m of team thread t after the last pass
   __host__ __device__ static constexpr int bin_of(int t, int m) { return t + T * m; }
+  // where the epilogue parks bin b of a team's accumulators in shared memory (consecutive lanes -> consecutive bins here)
+  __host__ __device__ static constexpr int pslot(int b) { return b; }
   // Bulk-copy (TMA) staging of the next frame pays off where a frame spans several warps and every
   // exchange is a multi-warp barrier (the hybrid plans); for the one-warp-per-frame sizes plain coalesced loads
   // are faster (same binary on the B200, packed-FP32 codelets: N = 1024 735.6 GS/s staged vs 751.7 plain,
@@ -131,7 +135,7 @@ struct Plan {
   static_assert(NT % UNIT_THREADS == 0 && (T <= 32 || UNITS <= 15), "units must tile the CTA (named barriers 1..15)");
   // epi_cta: the CTA-wide epilogue needs one row of segment sums and one feature row, not the per-unit two-slot ring
   static constexpr size_t smem_bytes(bool win, bool epi_cta, int seg_stride = CRN_MAX_SEGS, int band_stride = CRN_MAX_BANDS) {
-    return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win && WIN_SMEM ? N / 2 : 0)) +
+    return sizeof(float4) * (size_t)TW_SMEM + sizeof(float2) * ((size_t)TEAMS * XSZ + (win && WIN_SMEM ? N / 2 : 0)) +
            sizeof(float) * (epi_cta ? seg_stride + band_stride : 2 * UNITS * seg_stride + band_stride * UNITS) +
            sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
   }
@@ -175,13 +179,30 @@ struct HybridPlan {
 #ifndef CRN_WIN_CALC_MINC
 #define CRN_WIN_CALC_MINC 4
 #endif
-  static constexpr bool WIN_CALC = (C >= CRN_WIN_CALC_MINC);
+  static constexpr bool WIN_CALC_WANTED = (C >= CRN_WIN_CALC_MINC);
+  // Twiddle columns in tensor memory (round 3, crn_fft_regs.cuh "TMEM as a per-thread table store"): the 2 x 8 table
+  // rows a thread reads per frame (pass C: 32 wavefronts per 1024 samples, pass B: 8-12) leave the L1 / shared-memory
+  // pipe, the tables leave shared memory (so the per-thread pass-C table of FOLD_C costs nothing at N = 8192 either),
+  // and pass B loses its PRESCALE layer there (-32 packed instructions per frame and thread).  -DCRN_NO_TMEM_TW: A/B.
+#ifdef CRN_NO_TMEM_TW
+  static constexpr bool TMEM_TW = false;
+#else
+  static constexpr bool TMEM_TW = true;
+#endif
+  // Window pairs in tensor memory too (32 more columns per warp), in the order pass A consumes them.  Where the
+  // computed window is not a win (C = 2: the all-bins kernel loses 4 % to the extra FFMAs) the table leaves shared
+  // memory this way.  -DCRN_WIN_TMEM_MAXC=<C>: largest C that reads the window from TMEM (A/B; 0 = never).
+#ifndef CRN_WIN_TMEM_MAXC
+#define CRN_WIN_TMEM_MAXC 8
+#endif
+  static constexpr bool WIN_TMEM = TMEM_TW && (C <= CRN_WIN_TMEM_MAXC);
+  static constexpr bool WIN_CALC = WIN_CALC_WANTED && !WIN_TMEM;
 #if defined(CRN_FOLD_C_ALL)   // A/B switches (build.py --variant)
   static constexpr bool FOLD_C = true;
 #elif defined(CRN_FOLD_B_ALL)
   static constexpr bool FOLD_C = false;
 #else
-  static constexpr bool FOLD_C = (C < 8);
+  static constexpr bool FOLD_C = (C < 8) || TMEM_TW;
 #endif
   // C = 2: each warp keeps its own half of pass A's outputs (see the kernel); -DCRN_NO_OWN_SHARE: A/B switch
 #ifdef CRN_NO_OWN_SHARE
@@ -197,6 +218,20 @@ struct HybridPlan {
   static constexpr bool KEEP_OWN = (C > 2 && C <= CRN_KEEP_OWN);
   static constexpr int TW1 = FOLD_C ? 8 * T : 8 * 32;  // pass-C twisted-codelet table: 8 rows, one column per team thread / lane
   static constexpr int TW2 = 8 * C + (FOLD_C ? 0 : T);  // pass-B table: 8 rows, one column per warp (+ {u, u w^16} per thread)
+  static constexpr int TW_SMEM = TMEM_TW ? 0 : TW1 + TW2;  // tables staged in shared memory (none when they live in TMEM)
+  // The K-frame accumulators of the all-bins kernels in tensor memory as well (32 more columns): those kernels sit at
+  // the 128-register cap with 32 accumulators + 64 data registers live through all three passes, and whether ptxas
+  // spills, and how far it can hoist loads, moved N = 8192 by +-2 % from one harmless edit to the next.  With the
+  // accumulators parked in TMEM between frames (read - add - write back in four 8-column batches behind the last pass)
+  // the frame loop needs ~95 registers.  The kernels pruned to the reference band plan (10 accumulators) keep theirs in
+  // registers.  -DCRN_NO_ACC_TMEM: A/B.
+#ifdef CRN_NO_ACC_TMEM
+  static constexpr bool ACC_TMEM = false;
+#else
+  static constexpr bool ACC_TMEM = TMEM_TW;
+#endif
+  // columns per warp: 8 rows x 4 for pass C, the same for pass B, 16 window pairs, 32 accumulators
+  static constexpr int TMEM_COLS_PER_WARP = 64 + (WIN_TMEM || ACC_TMEM ? 32 : 0) + (ACC_TMEM ? 32 : 0);
   static constexpr int UNIT_THREADS = T;
   static constexpr int UNITS = TEAMS;
   static constexpr int TEAMS_PER_UNIT = 1;
@@ -207,26 +242,32 @@ struct HybridPlan {
   // +4 % at N = 2048, +15 % at 4096, but -3 % at 8192, where the staged copy (one more shared-memory write and
   // read of the whole frame) meets a shared-memory pipe that is already ~70 % busy - there plain coalesced loads
   // behind the L2 prefetch win (435 -> 450 GS/s with 64 sub-channels, 467 -> 482 with the reference bands).
-#ifdef CRN_TMA_8192  // A/B switch
-  static constexpr bool TMA = true;
-#else
-  static constexpr bool TMA = (C < 8);
+  // Round 3: once the prefetch no longer sits in front of the loads and the tables left shared memory, plain loads win
+  // at every hybrid size (same box, CRN_NO_TMA toggled: 4096 613 -> 635 GS/s reference bands, 543 -> 557 all bins;
+  // 2048 705 -> 709 / 618 -> 618): the staged frame's extra write + read of shared memory costs more than the load
+  // latency it hides.  The staging code stays (parity-tested); -DCRN_TMA_MAXC=<C> compiles it in for C <= that (A/B).
+#ifndef CRN_TMA_MAXC
+#define CRN_TMA_MAXC 0
 #endif
+  static constexpr bool TMA = (C <= CRN_TMA_MAXC);
   // The window table (8 / 16 / 32 KB) lives in shared memory.  With one frame per CTA the two large ones were what
   // kept another CTA off the SM and were read through the read-only L1 path instead; with two frames per CTA
   // (4096: 2 CTAs/SM, 8192: 1) they fit, and shared memory is the faster home: 4096 +2 % (reference bands) /
   // +4 % (64 sub-channels), 8192 -1 % / +5 %.  -DCRN_WIN_L1 restores the L1 path from 4096 up (A/B).
 #ifdef CRN_WIN_L1
-  static constexpr bool WIN_SMEM = (N < 4096) && !WIN_CALC;
+  static constexpr bool WIN_SMEM = (N < 4096) && !WIN_CALC && !WIN_TMEM;
 #else
-  static constexpr bool WIN_SMEM = !WIN_CALC;
+  static constexpr bool WIN_SMEM = !WIN_CALC && !WIN_TMEM;
 #endif
   static constexpr bool PREFETCH = true;           // hybrid plans: +2 % (2048) ... +5 % (8192) with
   static_assert(C == 2 || C == 4 || C == 8, "hybrid plans cover N = 2048, 4096, 8192");
   static_assert(UNITS <= 15, "named barriers 1..15");
   __host__ __device__ static constexpr int bin_of(int t, int m) { return C * ((t & 31) + 32 * m) + (t >> 5); }
+  // Consecutive lanes hold bins C apart: parked at b they would hit 32 / C banks (ncu, N = 8192: 8 wavefronts per store,
+  // 2 % of the kernel's shared-memory traffic); one pad word per 32 spreads them over all 32 banks.
+  __host__ __device__ static constexpr int pslot(int b) { return b + (b >> 5); }
   static constexpr size_t smem_bytes(bool win, bool epi_cta, int seg_stride = CRN_MAX_SEGS, int band_stride = CRN_MAX_BANDS) {
-    return sizeof(float4) * (size_t)(TW1 + TW2) + sizeof(float2) * ((size_t)TEAMS * XSZ + (win && WIN_SMEM ? N / 2 : 0)) +
+    return sizeof(float4) * (size_t)TW_SMEM + sizeof(float2) * ((size_t)TEAMS * XSZ + (win && WIN_SMEM ? N / 2 : 0)) +
            sizeof(float) * (epi_cta ? seg_stride + band_stride : 2 * UNITS * seg_stride + band_stride * UNITS) +
            sizeof(int) * 4 * UNITS + 8 * TEAMS + 8;
   }
@@ -296,6 +337,13 @@ __device__ __forceinline__ void tma_load_frame(void *dst_smem, const void *src_g
                : "memory");
 }
 
+// TMEM allocations are a power of two of columns, at least 32
+__host__ __device__ constexpr unsigned tmem_alloc_cols(int need) {
+  unsigned c = 32;
+  while ((int)c < need) c *= 2;
+  return c;
+}
+
 template <int T>
 __device__ __forceinline__ void team_sync(int team) {
   if constexpr (T == 32) {
@@ -319,20 +367,45 @@ __device__ __forceinline__ float hann_calc(float2 seed) {
   constexpr float hs = (float)(0.5 * cx_sin_turn(M * T, N - 1));
   return fmaf(seed.y, hs, fmaf(seed.x, hc, 0.5f));
 }
-enum { WIN_NONE = 0, WIN_TABLE = 1, WIN_COMPUTED = 2 };
+enum { WIN_NONE = 0, WIN_TABLE = 1, WIN_COMPUTED = 2, WIN_IN_TMEM = 3 };
+// Position of window pair m0 (registers m0, m0 + E/2) in the thread's TMEM window columns: the R/2 pairs of codelet
+// I = m0 % G are consecutive (pass A reads them with one tcgen05.ld), G = E / R.
+__host__ __device__ constexpr int win_tmem_pos(int m0, int G, int R) { return (m0 % G) * (R / 2) + m0 / G; }
+
 
 // Pass 0: E/R radix-R FFTs on registers {i + q*(E/R)}; the window (if any) rides on the first stage.
 template <int E, int R, int T, int WMODE>
 __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__restrict__ winp, int t,
-                                               float2 wseed = make_float2(0.f, 0.f)) {
+                                               float2 wseed = make_float2(0.f, 0.f), unsigned twin = 0) {
   constexpr int G = E / R;
   constexpr int LOG = ilog2(R);
+  // WIN_IN_TMEM: the R/2 window pairs of a codelet are one tcgen05.ld (R = 4: one row, R = 8: two), fetched one codelet ahead
+  typename std::conditional<R == 8, TmemPending8, TmemPending4>::type wpend;
+  if constexpr (WMODE == WIN_IN_TMEM) {
+    static_assert(R == 4 || R == 8, "TMEM window: radix-4 / radix-8 first pass");
+    if constexpr (R == 8) wpend = tmem_issue8(twin);
+    else wpend = tmem_issue4(twin);
+  }
   static_for<0, G>([&](auto I) {
     float2 v[R];
+    float4 wq[2];
+    if constexpr (WMODE == WIN_IN_TMEM) {
+      if constexpr (R == 8) {
+        tmem_wait(wpend, wq[0], wq[1]);
+        if constexpr (I.value + 1 < G) wpend = tmem_issue8(twin + R * (I.value + 1));
+      } else {
+        wq[0] = tmem_wait(wpend);
+        if constexpr (I.value + 1 < G) wpend = tmem_issue4(twin + R * (I.value + 1));
+      }
+    }
     static_for<0, R / 2>([&](auto Q) {
       constexpr int m0 = I.value + Q.value * G;  // partner is register m0 + E/2
       constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
-      if constexpr (WMODE == WIN_TABLE) {
+      if constexpr (WMODE == WIN_IN_TMEM) {
+        const float4 w4 = wq[Q.value / 2];
+        if constexpr (Q.value & 1) butterfly_w_real(a[m0], a[m0 + E / 2], w4.z, w4.w, v[br], v[br + 1]);
+        else butterfly_w_real(a[m0], a[m0 + E / 2], w4.x, w4.y, v[br], v[br + 1]);
+      } else if constexpr (WMODE == WIN_TABLE) {
         const float2 w = winp[m0 * T + t];
         butterfly_w_real(a[m0], a[m0 + E / 2], w.x, w.y, v[br], v[br + 1]);
       } else if constexpr (WMODE == WIN_COMPUTED) {
@@ -371,7 +444,8 @@ __device__ __forceinline__ void reg_pass_twisted(float2 (&a)[E], const float4 *_
         butterfly_w_cplx<false>(a[m0], a[m0 + E / 2], make_float2(uu.x, uu.y), make_float2(uu.z, uu.w), v[br], v[br + 1]);
       });
     } else {
-    const float2 tau = tw.template entry<0>();  // w^(R/2): every first-stage butterfly
+    const float4 r0 = tw.template row<0>();
+    const float2 tau = make_float2(r0.x, r0.y);  // w^(R/2): every first-stage butterfly
     static_for<0, R / 2>([&](auto Q) {
       constexpr int m0 = I.value + Q.value * G;  // partner is register m0 + E/2
       constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
@@ -380,9 +454,23 @@ __device__ __forceinline__ void reg_pass_twisted(float2 (&a)[E], const float4 *_
       butterfly_rt(v[br], v[br + 1], tau.x, -tau.y);
     });
     }
-    fft_dit_twisted<R, 2, RS>(v, tw);
+    fft_dit_twisted<R, 2>(v, tw);
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
+}
+
+// The same pass with the thread's twiddle column held in tensor memory (one radix-R codelet per thread: E == R).
+template <int R>
+__device__ __forceinline__ void reg_pass_twisted_tmem(float2 (&a)[R], unsigned taddr) {
+  constexpr int LOG = ilog2(R);
+  float2 v[R];
+  static_for<0, R / 2>([&](auto Q) {
+    constexpr int br = bitrev(Q.value, LOG);  // even; bitrev(Q + R/2) == br + 1
+    v[br] = a[Q.value];
+    v[br + 1] = a[Q.value + R / 2];
+  });
+  fft_dit_twisted_tmem<R>(v, taddr);
+  static_for<0, R>([&](auto Q) { a[Q.value] = v[Q.value]; });
 }
 
 // Exchange rows are padded by two points: rows stay 16-byte aligned for the 16-byte stores of pass 0 and
@@ -537,12 +625,13 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
   constexpr bool PREFETCH = P::PREFETCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *tw1 = reinterpret_cast<float4 *>(smem_raw);
-  float4 *tw2 = tw1 + P::TW1;
-  float2 *xbuf = reinterpret_cast<float2 *>(tw2 + P::TW2);
+  float4 *tw2 = tw1 + P::TW1;                                  // (both unused when the tables live in TMEM)
+  float2 *xbuf = reinterpret_cast<float2 *>(tw1 + P::TW_SMEM);
   float2 *winp_s = xbuf + (size_t)TEAMS * P::XSZ;
   constexpr bool WSM = WIN && P::WIN_SMEM;
   const float2 *winp = WSM ? winp_s : prm.winp;  // window pairs: shared copy, or read-only global path
-  constexpr int WMODE = !WIN ? WIN_NONE : (P::WIN_CALC ? WIN_COMPUTED : WIN_TABLE);
+  constexpr bool ACC_IN_TMEM = P::ACC_TMEM && AMASK == full_acc_mask<P::E>() && P::E % 8 == 0;
+  constexpr int WMODE = !WIN ? WIN_NONE : (P::WIN_TMEM ? WIN_IN_TMEM : (P::WIN_CALC ? WIN_COMPUTED : WIN_TABLE));
   // unit epilogue: [2][UNITS][seg_stride] partial sums + [UNITS][band_stride] features; CTA epilogue: one row each
   float *segpart = reinterpret_cast<float *>(winp_s + (WSM ? N / 2 : 0));
   const int SEGS = prm.seg_stride, BANDS = prm.band_stride;  // row lengths (the launch sized the allocation with them)
@@ -572,7 +661,41 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
   float *part = reinterpret_cast<float *>(xbuf + (size_t)(unit * TPU) * P::XSZ);  // unit's N floats
 
   // one-time table staging (persistent CTA: amortised over all its groups)
-  for (int i = tid; i < P::TW1 + P::TW2; i += NT) tw1[i] = prm.tw[i];
+  for (int i = tid; i < P::TW_SMEM; i += NT) tw1[i] = prm.tw[i];
+  unsigned tmem_tw = 0;  // TMEM address of this thread's twiddle rows (pass C: columns 0..31, pass B: 32..63)
+  unsigned tacc = 0;     // ... of its accumulators (columns 96..127), ACC_IN_TMEM
+  if constexpr (P::TMEM_TW) {
+    // one warp allocates 64 columns per warp that shares a lane quarter (NT/128 of them; a power of two >= 32)
+    constexpr unsigned COLS = tmem_alloc_cols(P::TMEM_COLS_PER_WARP * (NT / 128));
+    static_assert(NT % 128 == 0 && COLS <= 512, "TMEM allocation shape");
+    __shared__ unsigned tmem_base_s;
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned warp = (unsigned)tid >> 5;
+    tmem_tw = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (unsigned)P::TMEM_COLS_PER_WARP;
+    tacc = tmem_tw + 96;
+    // pass C (FOLD_C): column t of the first table; pass B: column r = t / 32 of the second (the same for a whole warp)
+    static_for<0, 8>([&](auto R) { tmem_st4(tmem_tw + 4 * R.value, prm.tw[R.value * T + t]); });
+    static_for<0, 8>([&](auto R) { tmem_st4(tmem_tw + 32 + 4 * R.value, prm.tw[P::TW1 + R.value * P::C + (t >> 5)]); });
+    if constexpr (WMODE == WIN_IN_TMEM) {
+      // window pairs, two per 16-byte store, in pass A's order (win_tmem_pos): columns 64 ..
+      constexpr int G0 = E / P::C;
+      static_for<0, E / 4>([&](auto PP) {
+        constexpr int p0 = 2 * PP.value, p1 = p0 + 1;
+        constexpr int ma = (p0 % (P::C / 2)) * G0 + p0 / (P::C / 2), mb = (p1 % (P::C / 2)) * G0 + p1 / (P::C / 2);
+        static_assert(win_tmem_pos(ma, G0, P::C) == p0 && win_tmem_pos(mb, G0, P::C) == p1, "window pair order");
+        const float2 wa = prm.winp[ma * T + t], wb = prm.winp[mb * T + t];
+        tmem_st4(tmem_tw + 64 + 2 * p0, make_float4(wa.x, wa.y, wb.x, wb.y));
+      });
+    }
+    tmem_wait_st();
+  }
   if constexpr (WSM)
     for (int i = tid; i < N / 2; i += NT) winp_s[i] = prm.winp[i];
   for (int i = tid; i < 4 * UNITS; i += NT) cnt[i] = 0;
@@ -604,9 +727,16 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
 
   int it = 0;
   for (long long w = (long long)blockIdx.x * GL + gl; w < prm.nwork; w += gstep, it++) {
-    float acc[E];
+    float acc[E];  // (ACC_IN_TMEM: only the epilogue below sees them in registers)
 #pragma unroll
     for (int m = 0; m < E; m++) acc[m] = 0.0f;
+    if constexpr (ACC_IN_TMEM) {
+      static_for<0, E / 8>([&](auto Cc) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        tmem_st8(tacc + 8 * Cc.value, z);
+      });
+      tmem_wait_st();
+    }
 
     // frame pointers advance by plain 64-bit adds inside the loop; the multiplications happen once per item
     const size_t fstep = (size_t)FT * (size_t)prm.stride;  // samples between this team's frames
@@ -668,9 +798,20 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           //    1's region, negating the wrapped one (W_N^(n + 1024) = -W_N^n), warp 1 stores value i into slot i.
           const int w = t >> 5;
           const float sg = w ? -1.0f : 1.0f;
+          float4 wq[2];  // WIN_IN_TMEM: four window pairs at a time, fetched one batch ahead
+          TmemPending8 wpend;
+          if constexpr (WMODE == WIN_IN_TMEM) wpend = tmem_issue8(tmem_tw + 64);
           static_for<0, E / 2>([&](auto I) {
             float2 p, q;
-            if constexpr (WMODE == WIN_TABLE) {
+            if constexpr (WMODE == WIN_IN_TMEM) {
+              if constexpr (I.value % 4 == 0) {
+                tmem_wait(wpend, wq[0], wq[1]);
+                if constexpr (I.value + 4 < E / 2) wpend = tmem_issue8(tmem_tw + 64 + 2 * (I.value + 4));
+              }
+              const float4 w4 = wq[(I.value % 4) / 2];
+              if constexpr (I.value & 1) butterfly_w_real(a[I.value], a[I.value + E / 2], w4.z, w4.w, p, q);
+              else butterfly_w_real(a[I.value], a[I.value + E / 2], w4.x, w4.y, p, q);
+            } else if constexpr (WMODE == WIN_TABLE) {
               const float2 wp = winp[I.value * T + t];  // { w[n], (+/-) w[n + N/2] }
               butterfly_w_real(a[I.value], a[I.value + E / 2], wp.x, wp.y, p, q);
             } else if constexpr (WMODE == WIN_COMPUTED) {
@@ -704,7 +845,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           // W_N^(-1024 r) = j^r (a swap and a sign).  The kept values are picked out of the radix-4 outputs by selects.
           // (C = 8, -DCRN_KEEP_OWN=8: the wrap factor W_N^(-1024 r) is an eighth turn - one complex multiply by a
           // constant for the one wrapped value per destination.)
-          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed);  // a[i + r G] = z_r[t + T i]
+          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64);  // a[i + r G] = z_r[t + T i]
           const int w = t >> 5;
           team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
           static_for<0, C>([&](auto W) {
@@ -745,7 +886,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
             static_for<1, C>([&](auto D) { a[C * I.value + D.value] = wb[((D.value - 1) * G + I.value) * 32 + lane]; });
           });
         } else {
-        reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed);
+        reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64);
         // the one team-wide exchange: y_r[n] (n = t + T*i) goes to warp r's region, linear in n
         team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
         static_for<0, G>([&](auto I) {
@@ -758,7 +899,8 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         // warp r: 1024-point FFT of y_r, warp-local from here on (same code as the N = 1024 kernel)
         __syncwarp();  // the region is rewritten in padded layout below
         // pass B: column j = lane, input q carries (W_N^(32 r))^q - the same w for the whole warp (table column r)
-        if constexpr (P::FOLD_C) reg_pass_twisted<E, 32, 32, 1, C>(a, tw2 + (t >> 5), 0);
+        if constexpr (P::TMEM_TW) reg_pass_twisted_tmem<32>(a, tmem_tw + 32);
+        else if constexpr (P::FOLD_C) reg_pass_twisted<E, 32, 32, 1, C>(a, tw2 + (t >> 5), 0);
         else reg_pass_twisted<E, 32, 32, 1, C, true>(a, tw2 + (t >> 5), 0, tw2 + 8 * C + t);
         exchange<E, 32, 32, 1, 5>(a, wb, lane, 0);
         if (tma && k + FT < KP) {
@@ -766,7 +908,8 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           if (t == 0) tma_load_frame(xb, x + fstep, frame_bytes, &mbars[team]);
         }
         // pass C: input q carries W_1024^(q lane) W_N^(q r) = (W_N^(C lane + r))^q: table column t = 32 r + lane
-        if constexpr (P::FOLD_C) reg_pass_twisted<E, 32, T, T, T>(a, tw1, t);
+        if constexpr (P::TMEM_TW) reg_pass_twisted_tmem<32>(a, tmem_tw);
+        else if constexpr (P::FOLD_C) reg_pass_twisted<E, 32, T, T, T>(a, tw1, t);
         else reg_pass_twisted<E, 32, 32, 32, 32>(a, tw1, lane);
       } else {
       // pass 0 (Ns = 1: no twiddles; window folded in)
@@ -790,6 +933,28 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
       }
       }  // !HYBRID
       // register m now holds bin P::bin_of(t, m)  (.cpp:152-154)
+      if constexpr (ACC_IN_TMEM) {
+        // accumulators live in tensor memory: eight at a time, the next batch in flight while this one is updated
+        tmem_wait_st();  // last frame's write-back (long done) before these columns are read again
+        TmemPending8 apend = tmem_issue8(tacc);
+        static_for<0, E / 8>([&](auto Cc) {
+          float v[8];
+          tmem_wait(apend, v);
+          if constexpr (Cc.value + 1 < E / 8) apend = tmem_issue8(tacc + 8 * (Cc.value + 1));
+          static_for<0, 8>([&](auto J) {
+            constexpr int m = 8 * Cc.value + J.value;
+            if constexpr (DET == DET_MAGSQ) {
+              v[J.value] = fmaf(a[m].x, a[m].x, v[J.value]);
+              v[J.value] = fmaf(a[m].y, a[m].y, v[J.value]);
+            } else {
+              float s;
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(a[m].x, a[m].x, a[m].y * a[m].y)));
+              v[J.value] += s;
+            }
+          });
+          tmem_st8(tacc + 8 * Cc.value, v);
+        });
+      } else
       static_for<0, E>([&](auto M) {
         constexpr int m = M.value;
         if constexpr ((AMASK >> m) & 1u) {
@@ -805,6 +970,14 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
       });
     }
 
+    if constexpr (ACC_IN_TMEM) {
+      tmem_wait_st();
+      static_for<0, E / 8>([&](auto Cc) {
+        float v[8];
+        tmem_wait(tmem_issue8(tacc + 8 * Cc.value), v);
+        static_for<0, 8>([&](auto J) { acc[8 * Cc.value + J.value] = v[J.value]; });
+      });
+    }
     const int S = (EPI == EPI_CTA) ? prm.split : 1;
     const long long g = (S == 1) ? w : w / S;  // decision group of this item
     const int ipart = (int)(w - g * S);        // which K/S-frame slice of it
@@ -815,7 +988,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
       {
         float *mypart = reinterpret_cast<float *>(xb);  // N floats per team, aliasing the exchange buffer
         static_for<0, E>([&](auto M) {
-          if constexpr ((AMASK >> M.value) & 1u) mypart[P::bin_of(t, M.value)] = acc[M.value];
+          if constexpr ((AMASK >> M.value) & 1u) mypart[P::pslot(P::bin_of(t, M.value))] = acc[M.value];
         });
       }
       __syncthreads();
@@ -832,7 +1005,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
               for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) {
 #pragma unroll
                 for (int q = 0; q < TEAMS; q++)
-                  sum[u] += reinterpret_cast<const float *>(xbuf + (size_t)q * P::XSZ)[i];
+                  sum[u] += reinterpret_cast<const float *>(xbuf + (size_t)q * P::XSZ)[P::pslot(i)];
               }
           }
 #pragma unroll
@@ -904,7 +1077,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
     unit_sync<T, UT>(unit);  // every thread of the unit is done reading its exchange buffer
     if (ut < T) {
       static_for<0, E>([&](auto M) {
-        if constexpr ((AMASK >> M.value) & 1u) part[P::bin_of(t, M.value)] = acc[M.value];
+        if constexpr ((AMASK >> M.value) & 1u) part[P::pslot(P::bin_of(t, M.value))] = acc[M.value];
       });
     }
     unit_sync<T, UT>(unit);
@@ -924,7 +1097,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         for (int u = 0; u < 4; u++) {
           const int s = sb + u * NWU;
           if (s < prm.nsegs)
-            for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) sum[u] += part[i];
+            for (int i = prm.seg_lo[s] + lane; i < prm.seg_hi[s]; i += 32) sum[u] += part[P::pslot(i)];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -973,6 +1146,13 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         __syncwarp();  // fb is reused by this warp's next combine
       }
     }
+    }
+  }
+  if constexpr (P::TMEM_TW) {
+    __syncthreads();  // every warp is done with its columns
+    if (tid < 32) {
+      constexpr unsigned COLS = tmem_alloc_cols(P::TMEM_COLS_PER_WARP * (NT / 128));
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_tw), "r"(COLS) : "memory");
     }
   }
 }
