@@ -89,7 +89,7 @@ struct Plan {
   static constexpr int UNITS = NT / UNIT_THREADS;  // reduction units per CTA
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
   static constexpr bool HYBRID = false;
-  static constexpr bool TMEM_TW = false, WIN_TMEM = false, ACC_TMEM = false;
+  static constexpr bool TMEM_TW = false, WIN_TMEM = false, ACC_TMEM = false, EARLY_FREE = false;
   static constexpr int C = 1;
   static constexpr int TW_SMEM = TW1 + TW2;        // float4 rows of the twiddle tables staged in shared memory
   // Window pairs from the table (false) or computed from two per-thread seeds (true; see HybridPlan::WIN_CALC).
@@ -250,6 +250,25 @@ struct HybridPlan {
 #define CRN_TMA_MAXC 0
 #endif
   static constexpr bool TMA = (C <= CRN_TMA_MAXC);
+  // "My region is free" is an mbarrier arrival, not a team barrier (round 3).  The team exchange used to be bracketed by
+  // two bar.sync: the first made sure every warp had gathered the previous frame's pass-B outputs out of its region
+  // before anyone overwrites it - but a warp reaches that point right after its gather, a whole pass C + accumulate +
+  // load + pass A before it needs the answer.  Each warp now arrives on the team's mbarrier after that gather and waits
+  // for the phase just before its first store of the next frame (already complete by then), so pass A's stores need no
+  // rendezvous and are issued codelet by codelet under the remaining butterflies; only the second barrier (stores
+  // visible -> gather) is left.  Shares mbars[] with the bulk-copy staging, hence not both.  Measured (same box,
+  // profiles/r03h_ab_tmem.txt): 2048 +1.9 % / +0.9 % (reference bands / all bins), 4096 +2.5 % / +1.4 %, 8192 -1.5 % /
+  // -3.3 % (eight warps per team: without the first rendezvous the second one waits longer than both did), so C <= 4;
+  // issuing pass A's stores codelet by codelet (EF_INTERLEAVE) changes nothing.  -DCRN_EARLY_FREE_MAXC=<C>: A/B.
+#ifndef CRN_EARLY_FREE_MAXC
+#define CRN_EARLY_FREE_MAXC 4
+#endif
+  static constexpr bool EARLY_FREE = !TMA && (C <= CRN_EARLY_FREE_MAXC);
+#ifdef CRN_EF_INTERLEAVE  // A/B: pass A's stores issued codelet by codelet (generic exchange, C = 8)
+  static constexpr bool EF_INTERLEAVE = true;
+#else
+  static constexpr bool EF_INTERLEAVE = false;
+#endif
   // The window table (8 / 16 / 32 KB) lives in shared memory.  With one frame per CTA the two large ones were what
   // kept another CTA off the SM and were read through the read-only L1 path instead; with two frames per CTA
   // (4096: 2 CTAs/SM, 8192: 1) they fit, and shared memory is the faster home: 4096 +2 % (reference bands) /
@@ -316,6 +335,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -374,9 +396,15 @@ __host__ __device__ constexpr int win_tmem_pos(int m0, int G, int R) { return (m
 
 
 // Pass 0: E/R radix-R FFTs on registers {i + q*(E/R)}; the window (if any) rides on the first stage.
-template <int E, int R, int T, int WMODE>
+struct NoAfter {
+  template <class I>
+  __device__ __forceinline__ void operator()(I) const {}
+};
+// `after(I)` runs once codelet I's outputs are back in a[] (the hybrid plans store them to the exchange there).
+template <int E, int R, int T, int WMODE, class After = NoAfter>
 __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__restrict__ winp, int t,
-                                               float2 wseed = make_float2(0.f, 0.f), unsigned twin = 0) {
+                                               float2 wseed = make_float2(0.f, 0.f), unsigned twin = 0,
+                                               After after = After()) {
   constexpr int G = E / R;
   constexpr int LOG = ilog2(R);
   // WIN_IN_TMEM: the R/2 window pairs of a codelet are one tcgen05.ld (R = 4: one row, R = 8: two), fetched one codelet ahead
@@ -418,6 +446,7 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
     });
     fft_dit<R, 2>(v);
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
+    after(I);
   });
 }
 
@@ -700,11 +729,22 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
     for (int i = tid; i < N / 2; i += NT) winp_s[i] = prm.winp[i];
   for (int i = tid; i < 4 * UNITS; i += NT) cnt[i] = 0;
   const bool tma = P::TMA && (EPI == EPI_CTA) && prm.use_tma;
+  static_assert(!(P::TMA && P::EARLY_FREE), "mbars[] serves either the bulk-copy staging or the region-free arrivals");
   if (tma && t == 0) {
     mbar_init(&mbars[team], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if constexpr (P::EARLY_FREE) {
+    if (t == 0) {
+      mbar_init(&mbars[team], T / 32);  // one arrival per warp of the team
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   __syncthreads();
+  unsigned free_phase = 0;
+  if constexpr (P::EARLY_FREE) {
+    if ((tid & 31) == 0) mbar_arrive(&mbars[team]);  // phase 0: nothing to wait for before the first frame
+  }
 
   const int L = prm.L, K = prm.K;
   const bool full = (L == N);
@@ -779,6 +819,11 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         // (spilled).  The empty asm makes the seeds opaque per frame, so the values are rebuilt where they are used.
         asm volatile("" : "+f"(wseed.x), "+f"(wseed.y));
       }
+      if constexpr (P::EARLY_FREE) {
+        // every warp of the team has gathered the previous frame's pass-B outputs: the regions may be overwritten
+        mbar_wait(&mbars[team], free_phase);
+        free_phase ^= 1u;
+      }
       if constexpr (P::HYBRID) {
         constexpr int C = P::C, G = E / C;
         // pass A: radix-C across the frame's C segments (window folded in).  The DIF twiddles W_N^(n r) that turn
@@ -826,7 +871,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           });
           a[E / 2] = mul2(a[E / 2], bc2(-sg));  // warp 0: the value that wraps around in warp 1's shifted sequence
           float2 *theirs = xb + (1 - w) * P::RS + lane;
-          team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
+          if constexpr (!P::EARLY_FREE) team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
           theirs[w ? 0 : 32 * 15] = a[E / 2];
           static_for<1, E / 2>([&](auto I) { (theirs - (w ? 0 : 32))[32 * I.value] = a[I.value + E / 2]; });
           team_sync<T>(team);
@@ -847,7 +892,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           // constant for the one wrapped value per destination.)
           reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64);  // a[i + r G] = z_r[t + T i]
           const int w = t >> 5;
-          team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
+          if constexpr (!P::EARLY_FREE) team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
           static_for<0, C>([&](auto W) {
             if (w == W.value) {
               static_for<0, C>([&](auto R) {
@@ -886,12 +931,18 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
             static_for<1, C>([&](auto D) { a[C * I.value + D.value] = wb[((D.value - 1) * G + I.value) * 32 + lane]; });
           });
         } else {
-        reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64);
         // the one team-wide exchange: y_r[n] (n = t + T*i) goes to warp r's region, linear in n
-        team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
-        static_for<0, G>([&](auto I) {
-          static_for<0, C>([&](auto R) { xb[R.value * P::RS + t + T * I.value] = a[I.value + R.value * G]; });
-        });
+        if constexpr (P::EARLY_FREE && P::EF_INTERLEAVE) {
+          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64, [&](auto I) {
+            static_for<0, C>([&](auto R) { xb[R.value * P::RS + t + T * I.value] = a[I.value + R.value * G]; });
+          });
+        } else {
+          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64);
+          if constexpr (!P::EARLY_FREE) team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
+          static_for<0, G>([&](auto I) {
+            static_for<0, C>([&](auto R) { xb[R.value * P::RS + t + T * I.value] = a[I.value + R.value * G]; });
+          });
+        }
         team_sync<T>(team);
 #pragma unroll
         for (int m = 0; m < E; m++) a[m] = wb[lane + 32 * m];
@@ -903,6 +954,10 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         else if constexpr (P::FOLD_C) reg_pass_twisted<E, 32, 32, 1, C>(a, tw2 + (t >> 5), 0);
         else reg_pass_twisted<E, 32, 32, 1, C, true>(a, tw2 + (t >> 5), 0, tw2 + 8 * C + t);
         exchange<E, 32, 32, 1, 5>(a, wb, lane, 0);
+        if constexpr (P::EARLY_FREE) {
+          __syncwarp();  // every lane's gather is done: this warp's region is free for the next frame's exchange
+          if (lane == 0) mbar_arrive(&mbars[team]);
+        }
         if (tma && k + FT < KP) {
           team_sync<T>(team);  // every warp of the team has gathered its points: the regions are idle
           if (t == 0) tma_load_frame(xb, x + fstep, frame_bytes, &mbars[team]);
