@@ -497,6 +497,16 @@ int crn_create(const crn_config *cfg, crn_handle **out) {
     b.seg_lo[s] = (short)cfg->segs[s].lo;
     b.seg_hi[s] = (short)cfg->segs[s].hi;
   }
+  {  // segments listed band by band (non-decreasing band index)?  then band b owns a contiguous run of entries
+    b.bands_contig = 1;
+    for (int s = 1; s < cfg->nsegs; s++)
+      if (cfg->segs[s].band < cfg->segs[s - 1].band) b.bands_contig = 0;
+    int s = 0;
+    for (int band = 0; band <= cfg->nbands && band <= CRN_MAX_BANDS; band++) {
+      while (b.bands_contig && s < cfg->nsegs && cfg->segs[s].band < band) s++;
+      b.band_first[band] = (short)s;
+    }
+  }
   {  // spectrum slices (accumulator registers) the band table reads: selects the pruned kernel when it can
     const crn::RadixPlan rp = crn::radix_plan(cfg->nfft);
     const int per_slice = cfg->nfft / rp.e;

@@ -72,6 +72,11 @@ struct SenseParams {
   double wih[CRN_ANN_INPUTS + 1][CRN_ANN_HIDDEN + 1];
   double who[CRN_ANN_HIDDEN + 1][CRN_ANN_OUTPUTS + 1];
   short seg_band[CRN_MAX_SEGS], seg_lo[CRN_MAX_SEGS], seg_hi[CRN_MAX_SEGS];
+  // Band b's segments are entries [band_first[b], band_first[b + 1]) when the table lists them band by band
+  // (bands_contig; every built-in plan does): the combine then walks its own segments instead of scanning all nsegs
+  // for every band (64 x 64 tests on one warp per decision in the 64-sub-channel plans).  Same additions, same order.
+  short band_first[CRN_MAX_BANDS + 1];
+  int bands_contig;
 };
 
 // Compile-time plan for one FFT size.
@@ -498,7 +503,14 @@ __device__ __forceinline__ void reg_pass_twisted_tmem(float2 (&a)[R], unsigned t
     v[br] = a[Q.value];
     v[br + 1] = a[Q.value + R / 2];
   });
+#ifdef CRN_NO_TMEM_PIPE  // A/B: every row fetched and waited for where it is used (no row in flight under the butterflies)
+  const TmemTwistedTable tw{taddr};
+  const float4 r0 = tw.template row<0>();
+  static_for<0, R / 2>([&](auto B) { butterfly_rt(v[2 * B.value], v[2 * B.value + 1], r0.x, -r0.y); });
+  fft_dit_twisted<R, 2>(v, tw);
+#else
   fft_dit_twisted_tmem<R>(v, taddr);
+#endif
   static_for<0, R>([&](auto Q) { a[Q.value] = v[Q.value]; });
 }
 
@@ -1102,8 +1114,12 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         if (decide) {
           for (int b = tid; b < prm.nbands; b += 32) {
             float m = 0.0f;
-            for (int sg = 0; sg < prm.nsegs; sg++)
-              if (prm.seg_band[sg] == b) m += segsum[sg];
+            if (prm.bands_contig) {
+              for (int sg = prm.band_first[b]; sg < prm.band_first[b + 1]; sg++) m += segsum[sg];
+            } else {
+              for (int sg = 0; sg < prm.nsegs; sg++)
+                if (prm.seg_band[sg] == b) m += segsum[sg];
+            }
             m *= prm.invK;
             const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
             featbuf[b] = f;
@@ -1183,9 +1199,14 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         const float *sp = segpart + ((size_t)slot * UNITS + (size_t)gl * upg) * SEGS;
         for (int b = lane; b < prm.nbands; b += 32) {
           float m = 0.0f;
-          for (int s = 0; s < prm.nsegs; s++)
-            if (prm.seg_band[s] == b)
+          if (prm.bands_contig) {
+            for (int s = prm.band_first[b]; s < prm.band_first[b + 1]; s++)
               for (int u = 0; u < upg; u++) m += sp[u * SEGS + s];
+          } else {
+            for (int s = 0; s < prm.nsegs; s++)
+              if (prm.seg_band[s] == b)
+                for (int u = 0; u < upg; u++) m += sp[u * SEGS + s];
+          }
           m *= prm.invK;
           const float f = (prm.postop == CRN_POST_SQUARE_OF_SUM) ? m * m : m;  // .cpp:194-197
           fb[b] = f;

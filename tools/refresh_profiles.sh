@@ -9,8 +9,8 @@ for f in bench_n1 bench_reference bench_wideband bench_multiradio bench_refexact
 cp gpurun_out/${tag}_latency.txt profiles/
 cp gpurun_out/${tag}_sweep.json profiles/${tag}_sweep.txt
 { echo "# Frame-loop opcode histograms (tools/sass_loop.py on libcrnsense.so as committed; static SASS, no GPU needed)"; echo
-  echo "Packed FP32 (\`FFMA2/FADD2/FMUL2\`) occupies the FP32 pipe for two cycles per warp instruction.  The bulk-copy (TMA) staging of the 2048/4096 plans shows up outside the histogram's top rows as \`UBLKCP\` / \`SYNCS\` ($(cuobjdump -sass $LIB | grep -c UBLKCP) \`UBLKCP\` in the library)."; echo
-  for pat in 'PlanILi1024ELi32ELi32ELi32ELi1ELi4ELi4EEELb1ELi1ELi0ELb0ELj2148284473E' 'PlanILi1024ELi32ELi32ELi32ELi1ELi4ELi4EEELb1ELi1ELi0ELb0ELj4294967295E' 'HybridPlanILi2048ELi4ELi2EEELb1ELi1ELi0ELb0ELj2148284473E' 'HybridPlanILi4096ELi2ELi2EEELb1ELi1ELi0ELb0ELj2148284473E' 'HybridPlanILi8192ELi2ELi1EEELb1ELi1ELi0ELb0ELj4294967295E' 'PlanILi512ELi32ELi32ELi16ELi1ELi8ELi4EEELb0ELi0ELi1ELb0ELj2148284473E'; do python tools/sass_loop.py $LIB "$pat" --md; done; } > profiles/${tag}_sass_frame_loops.md
+  echo "Packed FP32 (\`FFMA2/FADD2/FMUL2\`) occupies the FP32 pipe for two cycles per warp instruction.  \`LDTM\` / \`STTM\` are the tensor-memory reads / writes (tcgen05.ld / tcgen05.st: twiddle rows, window pairs, all-bins accumulators) of the hybrid plans ($(cuobjdump -sass $LIB | grep -c LDTM) \`LDTM\`, $(cuobjdump -sass $LIB | grep -c STTM) \`STTM\`, $(cuobjdump -sass $LIB | grep -c UTCATOMSWS) allocation instructions in the library; the bulk-copy staging of round 2 is no longer compiled in: $(cuobjdump -sass $LIB | grep -c UBLKCP) \`UBLKCP\`)."; echo
+  for pat in 'PlanILi1024ELi32ELi32ELi32ELi1ELi4ELi4EEELb1ELi1ELi0ELb0ELj2148284473E' 'PlanILi1024ELi32ELi32ELi32ELi1ELi4ELi4EEELb1ELi1ELi0ELb0ELj4294967295E' 'HybridPlanILi2048ELi4ELi2EEELb1ELi1ELi0ELb0ELj2148284473E' 'HybridPlanILi4096ELi2ELi2EEELb1ELi1ELi0ELb0ELj2148284473E' 'HybridPlanILi4096ELi2ELi2EEELb1ELi1ELi0ELb0ELj4294967295E' 'HybridPlanILi8192ELi2ELi1EEELb1ELi1ELi0ELb0ELj4294967295E' 'HybridPlanILi8192ELi2ELi1EEELb1ELi1ELi0ELb0ELj2148284473E' 'PlanILi512ELi32ELi32ELi16ELi1ELi8ELi4EEELb0ELi0ELi1ELb0ELj2148284473E'; do python tools/sass_loop.py $LIB "$pat" --md; done; } > profiles/${tag}_sass_frame_loops.md
 for k in 1024 2048 8192; do ncu -i gpurun_out/${tag}_sense_n$k.ncu-rep --page source --csv --print-source sass > /tmp/${tag}_src_$k.csv 2>/dev/null; done
 python - "$tag" <<'PY'
 import csv, collections, json, sys
