@@ -94,9 +94,25 @@ struct Plan {
   static constexpr int UNITS = NT / UNIT_THREADS;  // reduction units per CTA
   static constexpr int TEAMS_PER_UNIT = UNIT_THREADS / T;
   static constexpr bool HYBRID = false;
-  static constexpr bool TMEM_TW = false, WIN_TMEM = false, ACC_TMEM = false, EARLY_FREE = false;
+  static constexpr bool EARLY_FREE = false;
   static constexpr int C = 1;
-  static constexpr int TW_SMEM = TW1 + TW2;        // float4 rows of the twiddle tables staged in shared memory
+  // Pass-1 twiddle columns, window pairs and the all-bins accumulators in tensor memory, as in the hybrid plans (see
+  // HybridPlan::TMEM_TW): ncu puts the L1 / shared-memory data pipe of the N = 1024 kernel at 82 % busy with HBM at
+  // the copy peak - these reads are a quarter of its wavefronts (same box: 828 -> 859 GS/s with the reference bands,
+  // 750 -> 768 with 64 sub-channels, profiles/r02sl_ab_small_tmem.txt).  Two-pass plans whose team is a whole warp only:
+  // tcgen05.ld / st are warp-wide (.sync.aligned), and where two half-warp teams share a warp (N = 256 / 512) the
+  // unit epilogue lets them run different numbers of frames when K does not divide evenly - a diverged warp must not
+  // issue them (measured there anyway with balanced K: +1.5 ... +2.5 %; the K = 7 / 10 launches hang).
+  // -DCRN_SMALL_TMEM_MINN=<N>: smallest one-warp-per-frame size that does (A/B; 99999 = none).
+#ifndef CRN_SMALL_TMEM_MINN
+#define CRN_SMALL_TMEM_MINN 1024
+#endif
+  static constexpr bool TMEM_TW = (R2 == 1) && (T == 32) && (N >= CRN_SMALL_TMEM_MINN) && (NT % 128 == 0);
+  static constexpr bool WIN_TMEM = TMEM_TW, ACC_TMEM = TMEM_TW;
+  static constexpr int TM_TW = 0, TM_WIN = E, TM_ACC = 2 * E;   // first column of each table in a thread's TMEM row
+  static constexpr int TMEM_COLS_PER_WARP = 3 * E;
+  static constexpr int FIRST_RADIX = R0;                        // radix of the pass that consumes the window pairs
+  static constexpr int TW_SMEM = TMEM_TW ? 0 : TW1 + TW2;       // float4 rows of the twiddle tables staged in shared memory
   // Window pairs from the table (false) or computed from two per-thread seeds (true; see HybridPlan::WIN_CALC).
   // -DCRN_WIN_CALC_SMALL=<smallest N that computes>: A/B switch for the one-warp-per-frame plans.
 #ifdef CRN_WIN_CALC_SMALL
@@ -108,9 +124,9 @@ struct Plan {
   // are sensitive to how much of the SM's 256 KB is left as L1 (4 CTAs x 44 KB -> 196 KB carve-out; x 40 KB -> 164 KB:
   // +1.3 % at N = 1024, profiles/r02f_l1probe.txt; forcing the 228 KB carve-out costs 13-19 %).  -DCRN_PLAN_WIN_SMEM: A/B
 #ifdef CRN_PLAN_WIN_SMEM
-  static constexpr bool WIN_SMEM = !WIN_CALC;
+  static constexpr bool WIN_SMEM = !WIN_CALC && !WIN_TMEM;
 #else
-  static constexpr bool WIN_SMEM = (N < 512) && !WIN_CALC;
+  static constexpr bool WIN_SMEM = (N < 512) && !WIN_CALC && !WIN_TMEM;
 #endif
   // spectrum bin held in accumulator register m of team thread t after the last pass
   __host__ __device__ static constexpr int bin_of(int t, int m) { return t + T * m; }
@@ -168,40 +184,39 @@ struct HybridPlan {
   static constexpr int PADSHIFT = 5;
   static constexpr int RS = 32 * (32 + 2);         // float2 slots of one warp's region (padded 32x32 exchange)
   static constexpr int XSZ = C * RS;
-  // Where the q-independent part W_N^(j r) of the DIF twiddles goes (see above).  FOLD_C: into pass C's w - free, but
-  // the pass-C table then has one column per team thread (128 T bytes: 32 KB at N = 8192, which pushes the CTA past
-  // the 196 KB shared-memory carve-out and leaves the SM with a 28 KB L1: measured -8 %).  !FOLD_C (N = 8192): pass B
-  // multiplies its column by u = W_N^(j r) in its first stage (+32 packed instructions per frame and thread, one
-  // 16-byte read of {u, u w^16}); pass C then uses the 4 KB table of the 1024-point FFT.
-  // The Hann window is computed, not read (round 3): thread t needs w[t + T m] = 1/2 - 1/2 cos(theta_t + m Delta),
-  // theta_t = 2 pi t / (N - 1), Delta = 2 pi T / (N - 1), and cos(theta_t + m Delta) = cos(theta_t) cos(m Delta) -
-  // sin(theta_t) sin(m Delta) with cos / sin(m Delta) compile-time immediates and (cos, sin)(theta_t) two per-thread
-  // registers: two scalar FFMA per window value instead of half a 64-bit shared-memory read.  The hybrid kernels are
-  // bound by the L1 / shared-memory data pipe (ncu: 70 % busy at N = 8192, 84 % at 2048, the highest pipe of the SM),
-  // the window pairs were 32 of ~430 wavefronts per 1024 samples, and the table (N/2 float2: 16 / 32 KB) is what kept
-  // the FOLD_C table out of the 196 KB carve-out at N = 8192.  -DCRN_WIN_CALC_MINC=<C>: smallest C that computes (A/B;
-  // 99 = never).  Not at C = 2: the own-share exchange bakes a per-warp sign into the pairs.
-#ifndef CRN_WIN_CALC_MINC
-#define CRN_WIN_CALC_MINC 4
-#endif
-  static constexpr bool WIN_CALC_WANTED = (C >= CRN_WIN_CALC_MINC);
-  // Twiddle columns in tensor memory (round 3, crn_fft_regs.cuh "TMEM as a per-thread table store"): the 2 x 8 table
-  // rows a thread reads per frame (pass C: 32 wavefronts per 1024 samples, pass B: 8-12) leave the L1 / shared-memory
-  // pipe, the tables leave shared memory (so the per-thread pass-C table of FOLD_C costs nothing at N = 8192 either),
-  // and pass B loses its PRESCALE layer there (-32 packed instructions per frame and thread).  -DCRN_NO_TMEM_TW: A/B.
+  // Tables in tensor memory (crn_fft_regs.cuh "TMEM as a per-thread table store").  ncu on the round-2 kernels: the
+  // busiest pipe of the hybrid plans is the L1 / shared-memory data pipe (70 % at N = 8192, 84 % at 2048), and of its
+  // ~430 wavefronts per 1024 samples 32 were window pairs, 32 pass-C twiddle rows, 8-12 pass-B rows - loop-invariant
+  // values a thread re-reads every frame because 128 registers cannot hold them.  They now sit in the thread's own
+  // TMEM columns (tcgen05.st once per CTA, tcgen05.ld per frame: a different pipe), the tables leave shared memory
+  // (so the per-thread pass-C table of FOLD_C costs nothing at N = 8192 either and pass B loses its PRESCALE layer
+  // there: -32 packed instructions per frame and thread), and 8192 x 64 sub-channels went 465 -> 565 GS/s together
+  // with the other changes of this pass (profiles/r02s*_ab_*.txt).  -DCRN_NO_TMEM_TW: A/B.
 #ifdef CRN_NO_TMEM_TW
   static constexpr bool TMEM_TW = false;
 #else
   static constexpr bool TMEM_TW = true;
 #endif
-  // Window pairs in tensor memory too (32 more columns per warp), in the order pass A consumes them.  Where the
-  // computed window is not a win (C = 2: the all-bins kernel loses 4 % to the extra FFMAs) the table leaves shared
-  // memory this way.  -DCRN_WIN_TMEM_MAXC=<C>: largest C that reads the window from TMEM (A/B; 0 = never).
+  // Window pairs in TMEM too (32 more columns per warp), in the order pass A consumes them.
+  // -DCRN_WIN_TMEM_MAXC=<C>: largest C that reads the window from TMEM (A/B; 0 = never).
 #ifndef CRN_WIN_TMEM_MAXC
 #define CRN_WIN_TMEM_MAXC 8
 #endif
   static constexpr bool WIN_TMEM = TMEM_TW && (C <= CRN_WIN_TMEM_MAXC);
-  static constexpr bool WIN_CALC = WIN_CALC_WANTED && !WIN_TMEM;
+  // The alternative that led there, kept as a switch: the Hann window computed instead of read.  Thread t needs
+  // w[t + T m] = 1/2 - 1/2 cos(theta_t + m Delta), theta_t = 2 pi t / (N - 1), Delta = 2 pi T / (N - 1), and
+  // cos(theta_t + m Delta) = cos(theta_t) cos(m Delta) - sin(theta_t) sin(m Delta) with cos / sin(m Delta) compile-time
+  // immediates and (cos, sin)(theta_t) two per-thread registers: two scalar FFMA per window value (hann_calc).  Against
+  // the shared-memory table: 8192 +6 %, 4096 +3 %, 2048 +2 % / -4 % (reference bands / all bins), one-warp plans 0;
+  // against the TMEM table it loses 1-2 % (the FFMAs).  Used where WIN_TMEM is off and C >= CRN_WIN_CALC_MINC.
+#ifndef CRN_WIN_CALC_MINC
+#define CRN_WIN_CALC_MINC 4
+#endif
+  static constexpr bool WIN_CALC = (C >= CRN_WIN_CALC_MINC) && !WIN_TMEM;
+  // Where the q-independent part W_N^(j r) of the DIF twiddles goes (see above).  FOLD_C: into pass C's w - free, but
+  // the pass-C table then has one column per team thread (128 T bytes: 32 KB at N = 8192; in shared memory that pushed
+  // the CTA past the 196 KB carve-out: measured -8 %, so round 2 used !FOLD_C there: pass B multiplies its column by
+  // u = W_N^(j r) in its first stage, +32 packed instructions per frame and thread).  In TMEM the column is free.
 #if defined(CRN_FOLD_C_ALL)   // A/B switches (build.py --variant)
   static constexpr bool FOLD_C = true;
 #elif defined(CRN_FOLD_B_ALL)
@@ -237,6 +252,8 @@ struct HybridPlan {
 #endif
   // columns per warp: 8 rows x 4 for pass C, the same for pass B, 16 window pairs, 32 accumulators
   static constexpr int TMEM_COLS_PER_WARP = 64 + (WIN_TMEM || ACC_TMEM ? 32 : 0) + (ACC_TMEM ? 32 : 0);
+  static constexpr int TM_TW = 0, TM_TWB = 32, TM_WIN = 64, TM_ACC = 96;  // first column of each table in a thread's TMEM row
+  static constexpr int FIRST_RADIX = C;                                   // radix of the pass that consumes the window pairs
   static constexpr int UNIT_THREADS = T;
   static constexpr int UNITS = TEAMS;
   static constexpr int TEAMS_PER_UNIT = 1;
@@ -247,7 +264,7 @@ struct HybridPlan {
   // +4 % at N = 2048, +15 % at 4096, but -3 % at 8192, where the staged copy (one more shared-memory write and
   // read of the whole frame) meets a shared-memory pipe that is already ~70 % busy - there plain coalesced loads
   // behind the L2 prefetch win (435 -> 450 GS/s with 64 sub-channels, 467 -> 482 with the reference bands).
-  // Round 3: once the prefetch no longer sits in front of the loads and the tables left shared memory, plain loads win
+  // Second pass of round 2: once the prefetch no longer sits in front of the loads and the tables left shared memory, plain loads win
   // at every hybrid size (same box, CRN_NO_TMA toggled: 4096 613 -> 635 GS/s reference bands, 543 -> 557 all bins;
   // 2048 705 -> 709 / 618 -> 618): the staged frame's extra write + read of shared memory costs more than the load
   // latency it hides.  The staging code stays (parity-tested); -DCRN_TMA_MAXC=<C> compiles it in for C <= that (A/B).
@@ -255,14 +272,13 @@ struct HybridPlan {
 #define CRN_TMA_MAXC 0
 #endif
   static constexpr bool TMA = (C <= CRN_TMA_MAXC);
-  // "My region is free" is an mbarrier arrival, not a team barrier (round 3).  The team exchange used to be bracketed by
+  // "My region is free" is an mbarrier arrival, not a team barrier.  The team exchange used to be bracketed by
   // two bar.sync: the first made sure every warp had gathered the previous frame's pass-B outputs out of its region
   // before anyone overwrites it - but a warp reaches that point right after its gather, a whole pass C + accumulate +
   // load + pass A before it needs the answer.  Each warp now arrives on the team's mbarrier after that gather and waits
   // for the phase just before its first store of the next frame (already complete by then), so pass A's stores need no
-  // rendezvous and are issued codelet by codelet under the remaining butterflies; only the second barrier (stores
-  // visible -> gather) is left.  Shares mbars[] with the bulk-copy staging, hence not both.  Measured (same box,
-  // profiles/r03h_ab_tmem.txt): 2048 +1.9 % / +0.9 % (reference bands / all bins), 4096 +2.5 % / +1.4 %, 8192 -1.5 % /
+  // rendezvous; only the second barrier (stores visible -> gather) is left.  Shares mbars[] with the bulk-copy staging, hence not both.  Measured (same box,
+  // profiles/r02sh_ab_tmem.txt): 2048 +1.9 % / +0.9 % (reference bands / all bins), 4096 +2.5 % / +1.4 %, 8192 -1.5 % /
   // -3.3 % (eight warps per team: without the first rendezvous the second one waits longer than both did), so C <= 4;
   // issuing pass A's stores codelet by codelet (EF_INTERLEAVE) changes nothing.  -DCRN_EARLY_FREE_MAXC=<C>: A/B.
 #ifndef CRN_EARLY_FREE_MAXC
@@ -412,31 +428,34 @@ __device__ __forceinline__ void reg_pass_first(float2 (&a)[E], const float2 *__r
                                                After after = After()) {
   constexpr int G = E / R;
   constexpr int LOG = ilog2(R);
-  // WIN_IN_TMEM: the R/2 window pairs of a codelet are one tcgen05.ld (R = 4: one row, R = 8: two), fetched one codelet ahead
-  typename std::conditional<R == 8, TmemPending8, TmemPending4>::type wpend;
+  // WIN_IN_TMEM: the window pairs sit in TMEM in the order they are consumed (pair (I, Q) at position I R/2 + Q) and are
+  // fetched PPC pairs per tcgen05.ld (8 columns; 4 for a radix-4 pass), the next batch in flight under the butterflies
+  constexpr int PPC = (R == 4) ? 2 : 4;
+  typename std::conditional<PPC == 4, TmemPending8, TmemPending4>::type wpend;
+  float4 wq[2];
   if constexpr (WMODE == WIN_IN_TMEM) {
-    static_assert(R == 4 || R == 8, "TMEM window: radix-4 / radix-8 first pass");
-    if constexpr (R == 8) wpend = tmem_issue8(twin);
+    static_assert(R >= 4 && ((E / 2) % PPC) == 0, "TMEM window: whole batches of pairs");
+    if constexpr (PPC == 4) wpend = tmem_issue8(twin);
     else wpend = tmem_issue4(twin);
   }
   static_for<0, G>([&](auto I) {
     float2 v[R];
-    float4 wq[2];
-    if constexpr (WMODE == WIN_IN_TMEM) {
-      if constexpr (R == 8) {
-        tmem_wait(wpend, wq[0], wq[1]);
-        if constexpr (I.value + 1 < G) wpend = tmem_issue8(twin + R * (I.value + 1));
-      } else {
-        wq[0] = tmem_wait(wpend);
-        if constexpr (I.value + 1 < G) wpend = tmem_issue4(twin + R * (I.value + 1));
-      }
-    }
     static_for<0, R / 2>([&](auto Q) {
       constexpr int m0 = I.value + Q.value * G;  // partner is register m0 + E/2
       constexpr int br = bitrev(Q.value, LOG);   // even; bitrev(Q + R/2) == br + 1
       if constexpr (WMODE == WIN_IN_TMEM) {
-        const float4 w4 = wq[Q.value / 2];
-        if constexpr (Q.value & 1) butterfly_w_real(a[m0], a[m0 + E / 2], w4.z, w4.w, v[br], v[br + 1]);
+        constexpr int p = I.value * (R / 2) + Q.value;  // position of this pair in the thread's window columns
+        if constexpr (p % PPC == 0) {
+          if constexpr (PPC == 4) {
+            tmem_wait(wpend, wq[0], wq[1]);
+            if constexpr (p + PPC < E / 2) wpend = tmem_issue8(twin + 2 * (p + PPC));
+          } else {
+            wq[0] = tmem_wait(wpend);
+            if constexpr (p + PPC < E / 2) wpend = tmem_issue4(twin + 2 * (p + PPC));
+          }
+        }
+        const float4 w4 = wq[(p % PPC) / 2];
+        if constexpr (p & 1) butterfly_w_real(a[m0], a[m0 + E / 2], w4.z, w4.w, v[br], v[br + 1]);
         else butterfly_w_real(a[m0], a[m0 + E / 2], w4.x, w4.y, v[br], v[br + 1]);
       } else if constexpr (WMODE == WIN_TABLE) {
         const float2 w = winp[m0 * T + t];
@@ -494,6 +513,23 @@ __device__ __forceinline__ void reg_pass_twisted(float2 (&a)[E], const float4 *_
 }
 
 // The same pass with the thread's twiddle column held in tensor memory (one radix-R codelet per thread: E == R).
+// E / R codelets per thread (codelet I on registers {I + q G}, its rows at taddr + I R): the one-warp-per-frame plans.
+template <int E, int R>
+__device__ __forceinline__ void reg_pass_twisted_tmem_multi(float2 (&a)[E], unsigned taddr) {
+  constexpr int G = E / R;
+  constexpr int LOG = ilog2(R);
+  static_for<0, G>([&](auto I) {
+    float2 v[R];
+    static_for<0, R / 2>([&](auto Q) {
+      constexpr int m0 = I.value + Q.value * G;
+      constexpr int br = bitrev(Q.value, LOG);
+      v[br] = a[m0];
+      v[br + 1] = a[m0 + E / 2];
+    });
+    fft_dit_twisted_tmem<R>(v, taddr + R * I.value);
+    static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
+  });
+}
 template <int R>
 __device__ __forceinline__ void reg_pass_twisted_tmem(float2 (&a)[R], unsigned taddr) {
   constexpr int LOG = ilog2(R);
@@ -720,19 +756,28 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned warp = (unsigned)tid >> 5;
     tmem_tw = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (unsigned)P::TMEM_COLS_PER_WARP;
-    tacc = tmem_tw + 96;
-    // pass C (FOLD_C): column t of the first table; pass B: column r = t / 32 of the second (the same for a whole warp)
-    static_for<0, 8>([&](auto R) { tmem_st4(tmem_tw + 4 * R.value, prm.tw[R.value * T + t]); });
-    static_for<0, 8>([&](auto R) { tmem_st4(tmem_tw + 32 + 4 * R.value, prm.tw[P::TW1 + R.value * P::C + (t >> 5)]); });
+    tacc = tmem_tw + P::TM_ACC;
+    if constexpr (P::HYBRID) {
+      // pass C (FOLD_C): column t of the first table; pass B: column r = t / 32 of the second (the same for a whole warp)
+      static_for<0, 8>([&](auto R) { tmem_st4(tmem_tw + P::TM_TW + 4 * R.value, prm.tw[R.value * T + t]); });
+      static_for<0, 8>([&](auto R) { tmem_st4(tmem_tw + 32 + 4 * R.value, prm.tw[P::TW1 + R.value * P::C + (t >> 5)]); });
+    } else {
+      // pass 1: codelet I of this thread works on column (t + T I) mod R0 of the table (R1/4 rows of R0 columns)
+      static_for<0, E / P::R1>([&](auto I) {
+        static_for<0, P::R1 / 4>([&](auto R) {
+          tmem_st4(tmem_tw + P::TM_TW + P::R1 * I.value + 4 * R.value, prm.tw[R.value * P::R0 + ((t + T * I.value) & (P::R0 - 1))]);
+        });
+      });
+    }
     if constexpr (WMODE == WIN_IN_TMEM) {
-      // window pairs, two per 16-byte store, in pass A's order (win_tmem_pos): columns 64 ..
-      constexpr int G0 = E / P::C;
+      // window pairs, two per 16-byte store, in the first pass's order (win_tmem_pos)
+      constexpr int RF = P::FIRST_RADIX, G0 = E / RF;
       static_for<0, E / 4>([&](auto PP) {
         constexpr int p0 = 2 * PP.value, p1 = p0 + 1;
-        constexpr int ma = (p0 % (P::C / 2)) * G0 + p0 / (P::C / 2), mb = (p1 % (P::C / 2)) * G0 + p1 / (P::C / 2);
-        static_assert(win_tmem_pos(ma, G0, P::C) == p0 && win_tmem_pos(mb, G0, P::C) == p1, "window pair order");
+        constexpr int ma = (p0 % (RF / 2)) * G0 + p0 / (RF / 2), mb = (p1 % (RF / 2)) * G0 + p1 / (RF / 2);
+        static_assert(win_tmem_pos(ma, G0, RF) == p0 && win_tmem_pos(mb, G0, RF) == p1, "window pair order");
         const float2 wa = prm.winp[ma * T + t], wb = prm.winp[mb * T + t];
-        tmem_st4(tmem_tw + 64 + 2 * p0, make_float4(wa.x, wa.y, wb.x, wb.y));
+        tmem_st4(tmem_tw + P::TM_WIN + 2 * p0, make_float4(wa.x, wa.y, wb.x, wb.y));
       });
     }
     tmem_wait_st();
@@ -817,7 +862,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
       if constexpr (PREFETCH) {
         // Pull the frame this team senses next towards L2: k + FT of this item, else its first frame of the CTA's next
         // item.  One frame of compute covers the DRAM latency, so the loads above hit L2.  Issued AFTER this frame's
-        // loads (round 3): the address used to be a select between two values kept alive across the whole frame loop -
+        // loads: the address used to be a select between two values kept alive across the whole frame loop -
         // spilled in the all-bins kernels, and the loads queued behind those local-memory reads (3 % of the N = 8192
         // kernel's warp time sat on that select); the item-boundary address is now rebuilt in its rare branch.
         // "+ (SPL-1) t" turns the per-thread sample pointer into a per-thread 128-byte line pointer.
@@ -857,13 +902,13 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           const float sg = w ? -1.0f : 1.0f;
           float4 wq[2];  // WIN_IN_TMEM: four window pairs at a time, fetched one batch ahead
           TmemPending8 wpend;
-          if constexpr (WMODE == WIN_IN_TMEM) wpend = tmem_issue8(tmem_tw + 64);
+          if constexpr (WMODE == WIN_IN_TMEM) wpend = tmem_issue8(tmem_tw + P::TM_WIN);
           static_for<0, E / 2>([&](auto I) {
             float2 p, q;
             if constexpr (WMODE == WIN_IN_TMEM) {
               if constexpr (I.value % 4 == 0) {
                 tmem_wait(wpend, wq[0], wq[1]);
-                if constexpr (I.value + 4 < E / 2) wpend = tmem_issue8(tmem_tw + 64 + 2 * (I.value + 4));
+                if constexpr (I.value + 4 < E / 2) wpend = tmem_issue8(tmem_tw + P::TM_WIN + 2 * (I.value + 4));
               }
               const float4 w4 = wq[(I.value % 4) / 2];
               if constexpr (I.value & 1) butterfly_w_real(a[I.value], a[I.value + E / 2], w4.z, w4.w, p, q);
@@ -902,7 +947,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
           // W_N^(-1024 r) = j^r (a swap and a sign).  The kept values are picked out of the radix-4 outputs by selects.
           // (C = 8, -DCRN_KEEP_OWN=8: the wrap factor W_N^(-1024 r) is an eighth turn - one complex multiply by a
           // constant for the one wrapped value per destination.)
-          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64);  // a[i + r G] = z_r[t + T i]
+          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + P::TM_WIN);  // a[i + r G] = z_r[t + T i]
           const int w = t >> 5;
           if constexpr (!P::EARLY_FREE) team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
           static_for<0, C>([&](auto W) {
@@ -945,11 +990,11 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         } else {
         // the one team-wide exchange: y_r[n] (n = t + T*i) goes to warp r's region, linear in n
         if constexpr (P::EARLY_FREE && P::EF_INTERLEAVE) {
-          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64, [&](auto I) {
+          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + P::TM_WIN, [&](auto I) {
             static_for<0, C>([&](auto R) { xb[R.value * P::RS + t + T * I.value] = a[I.value + R.value * G]; });
           });
         } else {
-          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + 64);
+          reg_pass_first<E, C, T, WMODE>(a, winp, t, wseed, tmem_tw + P::TM_WIN);
           if constexpr (!P::EARLY_FREE) team_sync<T>(team);  // every warp of the team is done with the previous frame's regions
           static_for<0, G>([&](auto I) {
             static_for<0, C>([&](auto R) { xb[R.value * P::RS + t + T * I.value] = a[I.value + R.value * G]; });
@@ -980,7 +1025,7 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
         else reg_pass_twisted<E, 32, 32, 32, 32>(a, tw1, lane);
       } else {
       // pass 0 (Ns = 1: no twiddles; window folded in)
-      reg_pass_first<E, P::R0, T, WMODE>(a, winp, t, wseed);
+      reg_pass_first<E, P::R0, T, WMODE>(a, winp, t, wseed, tmem_tw + P::TM_WIN);
       exchange<E, P::R0, T, 1, P::PADSHIFT>(a, xb, t, team);
       // after the frame's last exchange the buffer is free: start pulling this team's next frame now, so
       // the copy flies under the remaining butterflies and the accumulate
@@ -992,7 +1037,8 @@ __global__ void __launch_bounds__(P::NT, min_ctas<P, WIN, EPI, AMASK>()) sense_k
       };
       if constexpr (P::PASSES == 2) stage_next();
       // pass 1
-      reg_pass_twisted<E, P::R1, T, P::R0, P::R0>(a, tw1, t);
+      if constexpr (P::TMEM_TW) reg_pass_twisted_tmem_multi<E, P::R1>(a, tmem_tw + P::TM_TW);
+      else reg_pass_twisted<E, P::R1, T, P::R0, P::R0>(a, tw1, t);
       if constexpr (P::PASSES == 3) {
         exchange<E, P::R1, T, P::R0, P::PADSHIFT>(a, xb, t, team);
         stage_next();

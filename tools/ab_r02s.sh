@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-3 A/B pass on one box: GPU parity suite on the in-tree library, a parity subset on the keep-own-8 variant,
+# Round 2 (second session) A/B pass on one box: GPU parity suite on the in-tree library, a parity subset on the keep-own-8 variant,
 # then tools/ab_all.sh over the variants given (default: the set of the computed-window experiment).
-tag=${TAG:-r03a}
+tag=${TAG:-r02sa}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 python -m pytest tests -x -q -m gpu 2>&1 | tail -4

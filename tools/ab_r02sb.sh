@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-3 second A/B pass: computed window at C = 2 and for the one-warp-per-frame plans, bulk-copy staging at 8192 on
+# Round 2 (second session) second A/B pass: computed window at C = 2 and for the one-warp-per-frame plans, bulk-copy staging at 8192 on
 # top of the computed window; ncu --set full of the 8192 wideband kernel as built.
-tag=${TAG:-r03b}
+tag=${TAG:-r02sb}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3

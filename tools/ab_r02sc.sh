@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-3 third A/B pass: twiddle columns in tensor memory (main) against the same library without (notmem) and the
+# Round 2 (second session) third A/B pass: twiddle columns in tensor memory (main) against the same library without (notmem) and the
 # round-2 library (prev), hybrid sizes; GPU parity suite first.
-tag=${TAG:-r03c}
+tag=${TAG:-r02sc}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -5

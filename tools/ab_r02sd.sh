@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-3 fourth pass: window pairs in tensor memory (main: C = 2 only; wtm8: every hybrid size; wtm0: none),
+# Round 2 (second session) fourth pass: window pairs in tensor memory (main: C = 2 only; wtm8: every hybrid size; wtm0: none),
 # residency of a TMEM-using kernel (ncu occupancy section at N = 2048), GPU parity suite first.
-tag=${TAG:-r03d}
+tag=${TAG:-r02sd}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -4

@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-3 fifth pass: table rows fetched from TMEM one row ahead, plain loads at every hybrid size (main) against the
+# Round 2 (second session) fifth pass: table rows fetched from TMEM one row ahead, plain loads at every hybrid size (main) against the
 # previous build (wtm8) and keep-own at C = 8 on top (ko8); ncu --set full of the 8192 wideband kernel.
-tag=${TAG:-r03e}
+tag=${TAG:-r02se}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -4

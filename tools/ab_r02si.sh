@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-3: N = 8192 as one team per CTA, two CTAs per SM (t8192) at 1 / 4 / 8 / 16 waves of CTAs, against main.
-tag=${TAG:-r03i}
+# Round 2 (second session): N = 8192 as one team per CTA, two CTAs per SM (t8192) at 1 / 4 / 8 / 16 waves of CTAs, against main.
+tag=${TAG:-r02si}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 V=cognitive-radio-network_b200/variants

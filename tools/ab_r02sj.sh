@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-3: per-band segment ranges in the epilogue (small sizes, 64 sub-channels), TMEM rows with / without a row in
+# Round 2 (second session): per-band segment ranges in the epilogue (small sizes, 64 sub-channels), TMEM rows with / without a row in
 # flight at 8192; then compute-sanitizer over every kernel family.
-tag=${TAG:-r03j}
+tag=${TAG:-r02sj}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 {

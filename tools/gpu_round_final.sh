@@ -1,8 +1,8 @@
 #!/bin/bash
-# Final GPU pass of round 3: everything tools/gpu_round.sh produces, then racecheck of the 2048 / 4096 kernels with and
+# Final GPU pass of round 2 (second session): everything tools/gpu_round.sh produces, then racecheck of the 2048 / 4096 kernels with and
 # without the mbarrier hand-off (racecheck models bar.sync only: the hazards it lists must vanish in the variant that
 # keeps the team barrier).
-tag=${1:-r03k}
+tag=${1:-r02sk}
 tools/gpu_round.sh $tag
 V=$PWD/cognitive-radio-network_b200/variants
 {
