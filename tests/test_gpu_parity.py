@@ -629,6 +629,51 @@ def test_two_threads_two_handles(crn, oracle, torch):
     assert results["a"] == want and results["b"] == want and results["c"] == want
 
 
+def test_tensor_memory_kernels_share_an_sm(crn, oracle, torch):
+    """The N >= 1024 plans keep their tables (and all-bins accumulators) in tensor memory, allocated per CTA with
+    tcgen05.alloc.  Kernels of different handles launched on different streams may meet on one SM and compete for its
+    512 columns: an allocation may have to wait for a neighbour to finish, it must never deadlock or hand out columns
+    twice.  Three handles (1024 reference bands, 2048 x 64 channels, 4096 reference bands) run interleaved on three
+    streams, repeatedly; every result must equal the same handle's result when it ran alone."""
+    specs = [(1024, 8, "welch", 600), (2048, 4, "wide", 300), (4096, 4, "welch", 150)]
+    jobs = []
+    for nfft, navg, mode, ngroups in specs:
+        cfg = make_cfg(crn, nfft, navg, mode, nfft, 0)
+        gs = cfg.group_samples
+        iq, _ = oracle.synth(crn.synth_config(gs, dwell_groups=1, snr_db=10.0, seed=nfft), 4 * gs)
+        jobs.append(dict(want=oracle.sense_port(cfg, iq)))
+        iq = np.tile(iq, ngroups // 4)
+        jobs[-1].update(dict(cfg=cfg, ng=ngroups, iq=torch.from_numpy(np.ascontiguousarray(iq).view(np.float32)).cuda(),
+                         stream=torch.cuda.Stream()))
+    sensors = [crn.Sensor(j["cfg"], device=0) for j in jobs]
+    try:
+        def outs(j):
+            return (torch.empty(j["ng"], j["cfg"].nbands, dtype=torch.float32, device="cuda"),
+                    torch.empty(j["ng"], 3, dtype=torch.float64, device="cuda"),
+                    torch.empty(j["ng"], dtype=torch.int32, device="cuda"), torch.empty(j["ng"], dtype=torch.int64, device="cuda"))
+        alone = []
+        for s, j in zip(sensors, jobs):
+            o = outs(j)
+            s.sense_device(j["iq"], j["ng"], *o, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            alone.append([t.cpu().numpy() for t in o])
+            assert feat_close(alone[-1][0][:4], j["want"][0], FEAT_RTOL)
+        torch.cuda.synchronize()
+        for rep in range(6):
+            together = [outs(j) for j in jobs]
+            for s, j, o in zip(sensors, jobs, together):
+                j["stream"].wait_stream(torch.cuda.current_stream())
+                s.sense_device(j["iq"], j["ng"], *o, j["stream"].cuda_stream)
+            for j in jobs:
+                j["stream"].synchronize()
+            for a, o in zip(alone, together):
+                for x, y in zip(a, o):
+                    assert np.array_equal(x, y.cpu().numpy(), equal_nan=True)
+    finally:
+        for s in sensors:
+            s.close()
+
+
 def test_db_features(crn, oracle, torch):
     """Welch band power in dB: within 1e-3 dB of the oracle (north_star tolerance); the MLP still sees the
     linear powers, so decisions equal the linear-mode run."""
