@@ -137,3 +137,49 @@ def test_shard_groups_partition(crn):
                 assert f == pos
                 pos += c
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_library_is_sm100a_with_packed_fp32_and_tensor_memory():
+    """What the shipped binary is made of, checked on its SASS (no GPU needed): sm_100a cubins only; the FFT codelets
+    are packed FP32 (FFMA2); the N >= 1024 plans keep their tables in tensor memory (tcgen05.alloc / st / ld show up as
+    UTCATOMSWS / STTM / LDTM) and the N = 256 / 512 plans do not (two half-warp teams share a warp there and
+    tcgen05 is warp-wide); the frame loops of the headline kernels have no local-memory (spill) traffic."""
+    import shutil
+    import sys
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "cognitive-radio-network_b200", "libcrnsense.so")
+    elfs = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True, check=True).stdout
+    cubins = re.findall(r"ELF file\s+\d+:\s+(\S+)", elfs)
+    assert cubins and all(c.endswith(".sm_100a.cubin") for c in cubins), cubins
+    sys.path[:0] = [os.path.join(ROOT, "tools")]
+    import sass_loop
+    seen = {}
+    all_kernels = list(sass_loop.kernels(lib))
+    for name, ins in all_kernels:
+        m = re.search(r"sense_kernelINS_(?:10Hybrid)?(?:4)?PlanILi(\d+)E", name)
+        if not m:
+            continue
+        ops = [sass_loop.opname(t) for _, t in ins]
+        n = int(m.group(1))
+        d = seen.setdefault(n, dict(kernels=0, ffma2=0, ldtm=0, alloc=0))
+        d["kernels"] += 1
+        d["ffma2"] += ops.count("FFMA2")
+        d["ldtm"] += ops.count("LDTM")
+        d["alloc"] += ops.count("UTCATOMSWS")
+    assert sorted(seen) == [256, 512, 1024, 2048, 4096, 8192], sorted(seen)
+    for n, d in seen.items():
+        assert d["ffma2"] > 100 * d["kernels"], (n, d)
+        if n >= 1024:
+            assert d["ldtm"] > 0 and d["alloc"] >= d["kernels"], (n, d)
+        else:
+            assert d["ldtm"] == 0 and d["alloc"] == 0, (n, d)
+    # frame loops of the BASELINE kernels: configs[1] (1024, reference bands) and configs[2] (8192, all bins)
+    for pat in ("PlanILi1024ELi32ELi32ELi32ELi1ELi4ELi4EEELb1ELi1ELi0ELb0ELj2148284473E",
+                "HybridPlanILi8192ELi2ELi1EEELb1ELi1ELi0ELb0ELj4294967295E"):
+        hits = [(nm, ins) for nm, ins in all_kernels if pat in nm]
+        assert len(hits) == 1, pat
+        body = [sass_loop.opname(t) for _, t in sass_loop.frame_loop(hits[0][1])]
+        assert not any(o.startswith(("LDL", "STL")) for o in body), (pat, [o for o in body if o.startswith(("LDL", "STL"))])
+        assert body.count("FFMA2") > 300
