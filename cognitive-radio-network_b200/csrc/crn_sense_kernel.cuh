@@ -264,8 +264,8 @@ struct HybridPlan {
   // +4 % at N = 2048, +15 % at 4096, but -3 % at 8192, where the staged copy (one more shared-memory write and
   // read of the whole frame) meets a shared-memory pipe that is already ~70 % busy - there plain coalesced loads
   // behind the L2 prefetch win (435 -> 450 GS/s with 64 sub-channels, 467 -> 482 with the reference bands).
-  // Second pass of round 2: once the prefetch no longer sits in front of the loads and the tables left shared memory, plain loads win
-  // at every hybrid size (same box, CRN_NO_TMA toggled: 4096 613 -> 635 GS/s reference bands, 543 -> 557 all bins;
+  // Second pass of round 2: once the prefetch no longer sits in front of the loads and the tables left shared
+  // memory, plain loads win at every hybrid size (same box, CRN_NO_TMA toggled: 4096 613 -> 635 GS/s reference bands, 543 -> 557 all bins;
   // 2048 705 -> 709 / 618 -> 618): the staged frame's extra write + read of shared memory costs more than the load
   // latency it hides.  The staging code stays (parity-tested); -DCRN_TMA_MAXC=<C> compiles it in for C <= that (A/B).
 #ifndef CRN_TMA_MAXC
@@ -277,8 +277,8 @@ struct HybridPlan {
   // before anyone overwrites it - but a warp reaches that point right after its gather, a whole pass C + accumulate +
   // load + pass A before it needs the answer.  Each warp now arrives on the team's mbarrier after that gather and waits
   // for the phase just before its first store of the next frame (already complete by then), so pass A's stores need no
-  // rendezvous; only the second barrier (stores visible -> gather) is left.  Shares mbars[] with the bulk-copy staging, hence not both.  Measured (same box,
-  // profiles/r02sh_ab_tmem.txt): 2048 +1.9 % / +0.9 % (reference bands / all bins), 4096 +2.5 % / +1.4 %, 8192 -1.5 % /
+  // rendezvous; only the second barrier (stores visible -> gather) is left.  Shares mbars[] with the bulk-copy
+  // staging, hence not both.  Measured (same box, profiles/r02sh_ab_tmem.txt): 2048 +1.9 % / +0.9 % (reference bands / all bins), 4096 +2.5 % / +1.4 %, 8192 -1.5 % /
   // -3.3 % (eight warps per team: without the first rendezvous the second one waits longer than both did), so C <= 4;
   // issuing pass A's stores codelet by codelet (EF_INTERLEAVE) changes nothing.  -DCRN_EARLY_FREE_MAXC=<C>: A/B.
 #ifndef CRN_EARLY_FREE_MAXC
@@ -512,8 +512,8 @@ __device__ __forceinline__ void reg_pass_twisted(float2 (&a)[E], const float4 *_
   });
 }
 
-// The same pass with the thread's twiddle column held in tensor memory (one radix-R codelet per thread: E == R).
-// E / R codelets per thread (codelet I on registers {I + q G}, its rows at taddr + I R): the one-warp-per-frame plans.
+// The same pass with the thread's twiddle columns held in tensor memory.  E / R codelets per thread (codelet I on
+// registers {I + q G}, its rows at taddr + I R): the one-warp-per-frame plans.
 template <int E, int R>
 __device__ __forceinline__ void reg_pass_twisted_tmem_multi(float2 (&a)[E], unsigned taddr) {
   constexpr int G = E / R;
@@ -530,6 +530,7 @@ __device__ __forceinline__ void reg_pass_twisted_tmem_multi(float2 (&a)[E], unsi
     static_for<0, R>([&](auto Q) { a[I.value + Q.value * G] = v[Q.value]; });
   });
 }
+// One radix-R codelet per thread (E == R): passes B and C of the hybrid plans.
 template <int R>
 __device__ __forceinline__ void reg_pass_twisted_tmem(float2 (&a)[R], unsigned taddr) {
   constexpr int LOG = ilog2(R);
